@@ -1,0 +1,195 @@
+"""ctypes binding of the C ABI in include/dn_tensor.h.
+
+`CApi` binds one shared library exporting the operator entry points under a prefix: `dn_` for
+libdeepnet_b200.so (the product), `dno_` for the CPU oracle used by the tests. The struct layout below IS the ABI
+(`dn_tensor`, include/dn_tensor.h) — the F# binding declares the same sequential struct (fsharp/Native.fs).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import dtypes
+from .layout import TensorLayout
+
+DN_MAX_DIMS = 8
+
+# dn_status (include/dn_tensor.h) and the exception the reference raises in the same situation.
+DN_OK, DN_ERR_INVALID_ARG, DN_ERR_UNSUPPORTED, DN_ERR_OUT_OF_MEMORY, DN_ERR_INDEX_OUT_OF_RANGE, DN_ERR_CUDA, \
+    DN_ERR_NO_DEVICE, DN_ERR_SHAPE_MISMATCH = range(8)
+
+
+class CudaException(RuntimeError):
+    """ManagedCuda CudaException — CudaBackend.fs:28-38."""
+
+
+class OutOfCudaMemoryException(MemoryError):
+    """CudaUtils.fs:183-210."""
+
+
+class NotSupportedException(NotImplementedError):
+    """System.NotSupportedException — CudaBackend.fs:126-129."""
+
+
+_EXC = {
+    DN_ERR_INVALID_ARG: ValueError,
+    DN_ERR_UNSUPPORTED: NotSupportedException,
+    DN_ERR_OUT_OF_MEMORY: OutOfCudaMemoryException,
+    DN_ERR_INDEX_OUT_OF_RANGE: IndexError,
+    DN_ERR_CUDA: CudaException,
+    DN_ERR_NO_DEVICE: CudaException,
+    DN_ERR_SHAPE_MISMATCH: RuntimeError,  # InvalidOperationException
+}
+
+
+class dn_tensor(C.Structure):
+    _fields_ = [
+        ("base", C.c_void_p),
+        ("offset", C.c_int64),
+        ("ndims", C.c_int32),
+        ("dtype", C.c_int32),
+        ("shape", C.c_int64 * DN_MAX_DIMS),
+        ("stride", C.c_int64 * DN_MAX_DIMS),
+    ]
+
+
+def make_desc(base: int, layout: TensorLayout, dtype: int) -> dn_tensor:
+    if layout.NDims > DN_MAX_DIMS:
+        raise NotSupportedException(f"tensors of rank {layout.NDims} > {DN_MAX_DIMS} are not supported")
+    d = dn_tensor()
+    d.base = base
+    d.offset = layout.Offset
+    d.ndims = layout.NDims
+    d.dtype = dtype
+    for i, (s, st) in enumerate(zip(layout.Shape, layout.Stride)):
+        d.shape[i] = s
+        d.stride[i] = st
+    return d
+
+
+_P = C.POINTER(dn_tensor)
+_PP = C.POINTER(_P)
+
+# name -> argtypes, shared by both prefixes (operator entry points only)
+_OPERATOR_SIGNATURES = {
+    "fill_const": [_P, C.c_void_p],
+    "fill_incrementing": [_P, C.c_void_p, C.c_void_p],
+    "copy": [_P, _P],
+    "convert": [_P, _P],
+    "unary": [C.c_int32, _P, _P],
+    "binary": [C.c_int32, _P, _P, _P],
+    "compare": [C.c_int32, _P, _P, _P],
+    "is_finite": [_P, _P],
+    "if_then_else": [_P, _P, _P, _P],
+    "reduce_last_axis": [C.c_int32, _P, _P],
+    "arg_reduce_last_axis": [C.c_int32, _P, _P],
+    "find_last_axis": [C.c_void_p, _P, _P],
+    "gather": [_P, _PP, C.c_int32, _P],
+    "scatter": [_P, _PP, C.c_int32, _P],
+    "count_true": [_P, C.POINTER(C.c_int64)],
+    "masked_get": [_P, _P, _PP, C.c_int32],
+    "masked_set": [_P, _PP, C.c_int32, _P],
+    "true_indices": [_P, _P],
+    "vec_vec_dot": [_P, _P, _P],
+    "mat_vec_dot": [_P, _P, _P],
+    "mat_mat_dot": [_P, _P, _P],
+    "batched_mat_mat_dot": [_P, _P, _P],
+}
+
+# device / storage entry points exported only by the product library
+_DEVICE_SIGNATURES = {
+    "init": [C.c_int32],
+    "device_count": [C.POINTER(C.c_int32)],
+    "set_device": [C.c_int32],
+    "get_device": [C.POINTER(C.c_int32)],
+    "set_stream": [C.c_void_p],
+    "get_stream": [C.POINTER(C.c_void_p)],
+    "sync": [],
+    "set_check_errors": [C.c_int32],
+    "poll_index_error": [C.POINTER(C.c_int32)],
+    "alloc": [C.c_int64, C.POINTER(C.c_void_p)],
+    "free": [C.c_void_p],
+    "alloc_host": [C.c_int64, C.POINTER(C.c_void_p)],
+    "free_host": [C.c_void_p],
+    "memset_zero": [C.c_void_p, C.c_int64],
+    "memcpy_h2d": [C.c_void_p, C.c_void_p, C.c_int64],
+    "memcpy_d2h": [C.c_void_p, C.c_void_p, C.c_int64],
+    "memcpy_d2d": [C.c_void_p, C.c_void_p, C.c_int64],
+    "get_item": [_P, C.POINTER(C.c_int64), C.c_void_p],
+    "set_item": [_P, C.POINTER(C.c_int64), C.c_void_p],
+    "arg_reduce_combine": [C.c_int32, _P, _P, _P],
+}
+
+ALL_PRODUCT_SYMBOLS = (
+    ["dn_" + n for n in _OPERATOR_SIGNATURES] + ["dn_" + n for n in _DEVICE_SIGNATURES] +
+    ["dn_last_error", "dn_launch_count", "dn_version"]
+)
+
+
+class CApi:
+    """One loaded shared library exposing the operator entry points under `prefix`."""
+
+    def __init__(self, path: str, prefix: str, with_device_api: bool):
+        if not os.path.exists(path):
+            raise ImportError(
+                f"native library {path} is missing — build it first (python -c 'import __graft_entry__ as g; "
+                f"g.build()' or `make`). There is no CPU fallback.")
+        self.path = path
+        self.prefix = prefix
+        self.lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        sigs = dict(_OPERATOR_SIGNATURES)
+        if with_device_api:
+            sigs.update(_DEVICE_SIGNATURES)
+        for name, argtypes in sigs.items():
+            fn = getattr(self.lib, prefix + name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int32
+            setattr(self, "_" + name, fn)
+        self._last_error = getattr(self.lib, prefix + "last_error")
+        self._last_error.restype = C.c_char_p
+        self._last_error.argtypes = []
+        if with_device_api:
+            self.lib.dn_launch_count.restype = C.c_int64
+            self.lib.dn_launch_count.argtypes = []
+            self.lib.dn_version.restype = C.c_char_p
+            self.lib.dn_version.argtypes = []
+
+    def check(self, status: int) -> None:
+        if status != DN_OK:
+            msg = (self._last_error() or b"").decode("utf-8", "replace")
+            raise _EXC.get(status, RuntimeError)(msg or f"native call failed with status {status}")
+
+    def call(self, name: str, *args) -> None:
+        self.check(getattr(self, "_" + name)(*args))
+
+
+def scalar_buffer(value, dtype: int):
+    """One host element of `dtype` as a ctypes-passable buffer (scalars are passed by pointer)."""
+    arr = np.array([value], dtype=dtypes.to_numpy(dtype))
+    return arr, arr.ctypes.data_as(C.c_void_p)
+
+
+def desc_ptr_array(descs: Sequence[Optional[dn_tensor]]):
+    """`const dn_tensor* const*` with NULL for None entries."""
+    arr = (_P * max(1, len(descs)))()
+    for i, d in enumerate(descs):
+        arr[i] = C.pointer(d) if d is not None else None
+    return arr
+
+
+_PRODUCT: Optional[CApi] = None
+
+
+def product_library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdeepnet_b200.so")
+
+
+def product() -> CApi:
+    """The product library. Fails loudly if it has not been built — there is no fallback path."""
+    global _PRODUCT
+    if _PRODUCT is None:
+        _PRODUCT = CApi(product_library_path(), "dn_", with_device_api=True)
+    return _PRODUCT
