@@ -1,0 +1,563 @@
+// reduce.cuh — last-axis reductions: Sum/Product/Min/Max/All/Any/CountTrue, ArgMin/ArgMax, Find
+// (Tensor/Tensor/TensorBackend.fs:125-135). Replaces Tensor/Tensor/Cuda/Kernels/Reduction.cuh:10-159, where ONE
+// thread folds a whole row serially and adjacent threads read addresses a row apart (5.3 GB/s on K40c).
+//
+// Semantics follow the HOST backend (Tensor/Tensor/Host/ScalarOps.fs:606-665), see SURVEY.md §8c rules 4, 5, 8:
+//   * ArgMin/ArgMax: strict compare, first occurrence, DN_NOT_FOUND when nothing beats the initial min/maxValue.
+//   * Min/Max on floats: `if res > v then res else v` from the FINITE initial value; a NaN replaces the running
+//     value and is itself replaced by the next element. This is an associative, order-sensitive monoid
+//     (value after the last NaN, saw-a-NaN flag); both kernel families below partition the axis into CONTIGUOUS,
+//     ORDERED pieces so it is reproduced exactly, not approximated.
+//   * Float Sum/Product: fixed-shape tree (deterministic run to run), within rel 1e-4*log2(n) of the host's
+//     left-to-right fold; integer folds wrap and are bit-exact in any order.
+//
+// Two kernel families, both HBM-bound by design:
+//   rows  — the reduced axis is contiguous (stride 1). A warp streams a contiguous part of a row with 128-bit
+//           loads (scalar head/tail peeled to 16-byte alignment), 4 loads in flight per lane, lane-interleaved
+//           inside a 32*VEC round, rounds in index order. A row is 1 part (warp per row), 8 parts (CTA per row,
+//           ordered combine in shared memory) or 8*S parts (S CTAs per row + finalize kernel) depending on R and L.
+//   cols  — the reduced axis is strided. Threads run along the flattened OUTER index sorted by source stride (so a
+//           warp reads consecutive addresses when some outer dim is contiguous) and each thread folds its chunk of
+//           the axis sequentially; the axis is split over threadIdx.y / blockIdx.y with an ordered combine.
+#pragma once
+
+#include "common.cuh"
+#include "ew_ops.cuh"
+
+namespace dn {
+
+constexpr int kRedThreads = 256;
+constexpr int kRedWarps = kRedThreads / 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Outer (non-reduced) dims in canonical form, innermost-first.
+struct RedOuter {
+    int32_t ndims;
+    uint32_t shape[DN_MAX_DIMS];
+    FastDiv div[DN_MAX_DIMS];
+    int64_t sstride[DN_MAX_DIMS];  // source, bytes
+    int64_t tstride[DN_MAX_DIMS];  // target, bytes
+};
+
+__device__ __forceinline__ void red_offsets(const RedOuter &o, uint32_t r, int64_t &soff, int64_t &toff) {
+    soff = 0;
+    toff = 0;
+    uint32_t rem = r;
+#pragma unroll
+    for (int d = 0; d < DN_MAX_DIMS; ++d) {
+        if (d >= o.ndims) break;
+        uint32_t q, x;
+        if (d == o.ndims - 1) {
+            x = rem;
+            q = 0;
+        } else {
+            q = o.div[d].div(rem);
+            x = rem - q * o.shape[d];
+        }
+        soff += (int64_t)x * o.sstride[d];
+        toff += (int64_t)x * o.tstride[d];
+        rem = q;
+    }
+}
+
+struct RedParams {
+    const char *src;
+    char *dst;
+    RedOuter outer;
+    uint32_t nrows;       // outputs in this launch
+    int64_t len;          // L
+    int64_t lstride;      // bytes per step along the reduced axis (cols family)
+    int32_t parts;        // rows: parts per row (1, 8 or 8*S); cols: chunks along the axis (blockDim.y*gridDim.y)
+    int64_t part_len;     // elements per part / chunk
+    void *partials;       // [nrows][ctas_per_row] states when more than one CTA shares a row
+    int32_t ctas_per_row;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Operators.  State must be trivially copyable.  `ordered` ops get the per-round NaN vote in the rows family.
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> __device__ __forceinline__ T shfl_xor_any(T v, int m) {
+    static_assert(sizeof(T) % 4 == 0 || sizeof(T) < 4, "state size");
+    if constexpr (sizeof(T) <= 4) {
+        unsigned u = 0;
+        memcpy(&u, &v, sizeof(T));
+        u = __shfl_xor_sync(kFull, u, m);
+        T r;
+        memcpy(&r, &u, sizeof(T));
+        return r;
+    } else {
+        constexpr int N = sizeof(T) / 4;
+        unsigned u[N];
+        memcpy(u, &v, sizeof(T));
+#pragma unroll
+        for (int i = 0; i < N; ++i) u[i] = __shfl_xor_sync(kFull, u[i], m);
+        T r;
+        memcpy(&r, u, sizeof(T));
+        return r;
+    }
+}
+
+template <class T>
+struct SumOp {
+    using In = T; using Out = T; using State = T;
+    static constexpr bool ordered = false;
+    __device__ static State identity() { return T(0); }
+    __device__ static void step(State &s, T v, int64_t) {
+        if constexpr (kIsInt<T>) s = (T)((UnsignedT<T>)s + (UnsignedT<T>)v);
+        else s = s + v;
+    }
+    __device__ static State combine(State a, State b) {
+        if constexpr (kIsInt<T>) return (T)((UnsignedT<T>)a + (UnsignedT<T>)b);
+        else return a + b;
+    }
+    __device__ static Out finalize(State s) { return s; }
+};
+
+template <class T>
+struct ProductOp {
+    using In = T; using Out = T; using State = T;
+    static constexpr bool ordered = false;
+    __device__ static State identity() { return T(1); }
+    __device__ static T mul(T a, T b) {
+        if constexpr (kIsInt<T> && sizeof(T) < 4) return (T)((uint32_t)(UnsignedT<T>)a * (uint32_t)(UnsignedT<T>)b);
+        else if constexpr (kIsInt<T>) return (T)((UnsignedT<T>)a * (UnsignedT<T>)b);
+        else return a * b;
+    }
+    __device__ static void step(State &s, T v, int64_t) { s = mul(s, v); }
+    __device__ static State combine(State a, State b) { return mul(a, b); }
+    __device__ static Out finalize(State s) { return s; }
+};
+
+// Integer Min/Max: plain lattice, identity == the host's initial value.
+template <class T, bool IsMax>
+struct MinMaxIntOp {
+    using In = T; using Out = T; using State = T;
+    static constexpr bool ordered = false;
+    __device__ static State identity() { return IsMax ? Limits<T>::lowest() : Limits<T>::max(); }
+    __device__ static void step(State &s, T v, int64_t) { s = IsMax ? (s > v ? s : v) : (s < v ? s : v); }
+    __device__ static State combine(State a, State b) { return IsMax ? (a > b ? a : b) : (a < b ? a : b); }
+    __device__ static Out finalize(State s) { return s; }
+};
+
+// Float Min/Max with the host's NaN behaviour (see header).  val: fold over the elements after the last NaN
+// (NaN itself if the piece ends with a NaN); flags bit0: piece contains a NaN, bit1: piece is non-empty.
+template <class T, bool IsMax>
+struct MinMaxFloatOp {
+    using In = T; using Out = T;
+    struct State { T val; int32_t flags; };
+    static constexpr bool ordered = true;
+    __device__ static T pos_inf() {
+        if constexpr (std::is_same<T, float>::value) return __int_as_float(0x7f800000);
+        else return __longlong_as_double(0x7ff0000000000000LL);
+    }
+    __device__ static T neutral() { return IsMax ? -pos_inf() : pos_inf(); }
+    __device__ static bool better(T a, T b) { return IsMax ? a > b : a < b; }  // `res > v` / `res < v`
+    __device__ static State identity() { return State{neutral(), 0}; }
+    // exact sequential step (ScalarOps.fs:620-628): if res `better` v then res else v
+    __device__ static void step(State &s, T v, int64_t) {
+        s.val = better(s.val, v) ? s.val : v;
+        s.flags |= 2 | (v != v ? 1 : 0);
+    }
+    __device__ static State combine(State a, State b) {  // a covers earlier indices than b
+        if (!(b.flags & 2)) return a;
+        if (!(a.flags & 2)) return b;
+        if (b.flags & 1) return State{b.val, 3};
+        return State{better(a.val, b.val) ? a.val : b.val, a.flags};
+    }
+    __device__ static Out finalize(State s) {
+        const T init = IsMax ? Limits<T>::lowest() : Limits<T>::max();
+        if (s.flags & 1) return s.val;
+        return better(init, s.val) ? init : s.val;
+    }
+};
+
+template <bool IsAll>
+struct AllAnyOp {
+    using In = bool8; using Out = bool8; using State = int32_t;
+    static constexpr bool ordered = false;
+    __device__ static State identity() { return IsAll ? 1 : 0; }
+    __device__ static void step(State &s, bool8 v, int64_t) { s = IsAll ? (s & (int)bool(v)) : (s | (int)bool(v)); }
+    __device__ static State combine(State a, State b) { return IsAll ? (a & b) : (a | b); }
+    __device__ static Out finalize(State s) { return bool8(s != 0); }
+};
+
+struct CountTrueOp {
+    using In = bool8; using Out = int64_t; using State = int64_t;
+    static constexpr bool ordered = false;
+    __device__ static State identity() { return 0; }
+    __device__ static void step(State &s, bool8 v, int64_t) { s += bool(v) ? 1 : 0; }
+    __device__ static State combine(State a, State b) { return a + b; }
+    __device__ static Out finalize(State s) { return s; }
+};
+
+template <class T, bool IsMax>
+struct ArgOp {
+    using In = T; using Out = int64_t;
+    struct State { T val; int64_t idx; };
+    static constexpr bool ordered = false;
+    __device__ static bool better(T a, T b) { return IsMax ? a > b : a < b; }
+    __device__ static State identity() {
+        return State{IsMax ? Limits<T>::lowest() : Limits<T>::max(), (int64_t)DN_NOT_FOUND};
+    }
+    __device__ static void step(State &s, T v, int64_t i) {
+        if (better(v, s.val)) { s.val = v; s.idx = i; }
+    }
+    __device__ static State combine(State a, State b) {
+        if (better(b.val, a.val) || (b.val == a.val && b.idx < a.idx && b.idx != (int64_t)DN_NOT_FOUND)) return b;
+        return a;
+    }
+    __device__ static Out finalize(State s) { return s.idx; }
+};
+
+template <class T>
+struct FindOp {
+    using In = T; using Out = int64_t; using State = int64_t;
+    static constexpr bool ordered = false;
+    T value;
+    __device__ static State identity() { return INT64_MAX; }
+    __device__ void stepv(State &s, T v, int64_t i) const {
+        bool eq;
+        if constexpr (kIsBool<T>) eq = bool(v) == bool(value);
+        else eq = v == value;
+        if (eq && i < s) s = i;
+    }
+    __device__ static State combine(State a, State b) { return a < b ? a : b; }
+    __device__ static Out finalize(State s) { return s == INT64_MAX ? (int64_t)DN_NOT_FOUND : s; }
+};
+
+// Uniform access to step (FindOp carries a runtime value, the others are stateless).
+template <class Op>
+__device__ __forceinline__ void op_step(const Op &op, typename Op::State &s, typename Op::In v, int64_t i) {
+    if constexpr (std::is_same<Op, FindOp<typename Op::In>>::value) op.stepv(s, v, i);
+    else Op::step(s, v, i);
+}
+
+template <class Op>
+__device__ __forceinline__ typename Op::State warp_combine_unordered(typename Op::State s) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) s = Op::combine(s, shfl_xor_any(s, m));
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rows family
+// ---------------------------------------------------------------------------------------------------------------
+// One warp folds elements [begin, end) of a contiguous row. All lanes return the same state.
+template <class Op>
+__device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const char *row, int64_t begin,
+                                                            int64_t end, int lane) {
+    using T = typename Op::In;
+    using State = typename Op::State;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int ROUND = 32 * VEC;
+    constexpr int UNR = 4;
+    State st = Op::identity();
+    int64_t last_nan = -1;  // ordered ops only: index of the last NaN seen by the WARP (uniform)
+    const T *p = reinterpret_cast<const T *>(row);
+
+    // one "round": lane handles n (<= VEC) consecutive elements starting at index i0 (or nothing if n == 0)
+    auto round = [&](const T *v, int n, int64_t i0) {
+        if constexpr (Op::ordered) {
+            int64_t my_nan = -1;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                if (j < n && v[j] != v[j]) my_nan = i0 + j;
+            if (__any_sync(kFull, my_nan >= 0)) {  // rare: a NaN in this round resets every lane
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) {
+                    int64_t o = __shfl_xor_sync(kFull, my_nan, m);
+                    my_nan = o > my_nan ? o : my_nan;
+                }
+                last_nan = my_nan;
+                st.val = Op::neutral();
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    if (j < n && i0 + j > last_nan) st.val = Op::better(st.val, v[j]) ? st.val : v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    if (j < n) st.val = Op::better(st.val, v[j]) ? st.val : v[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                if (j < n) op_step(op, st, v[j], i0 + j);
+        }
+    };
+
+    int64_t i = begin;
+    if (i < end) {
+        // scalar head up to 16-byte alignment
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(p + i);
+        int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
+        if (head > end - i) head = (int)(end - i);
+        if (head > 0) {
+            T v[VEC];
+            const bool on = lane < head;
+            if (on) v[0] = p[i + lane];
+            round(v, on ? 1 : 0, i + lane);
+            i += head;
+        }
+        // vector body, UNR rounds in flight
+        for (; i + (int64_t)ROUND * UNR <= end; i += (int64_t)ROUND * UNR) {
+            Pack<T, VEC> buf[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                buf[u] = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(p + i + (int64_t)u * ROUND + lane * VEC));
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) round(buf[u].v, VEC, i + (int64_t)u * ROUND + lane * VEC);
+        }
+        for (; i + ROUND <= end; i += ROUND) {
+            Pack<T, VEC> b = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(p + i + lane * VEC));
+            round(b.v, VEC, i + lane * VEC);
+        }
+        // tail: < ROUND elements, VEC rounds of scalar loads keep index order across rounds
+        for (; i < end; i += 32) {
+            T v[VEC];
+            const bool on = i + lane < end;
+            if (on) v[0] = p[i + lane];
+            round(v, on ? 1 : 0, i + lane);
+        }
+    }
+    if constexpr (Op::ordered) {
+        // lane values -> warp value; NaN bookkeeping is already warp-uniform
+        T v = st.val;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            T o = __shfl_xor_sync(kFull, v, m);
+            v = Op::better(v, o) ? v : o;
+        }
+        State out;
+        out.flags = (end > begin ? 2 : 0) | (last_nan >= 0 ? 1 : 0);
+        out.val = v;
+        if (last_nan >= 0 && last_nan == end - 1) out.val = p[last_nan];  // piece ends with the NaN itself
+        return out;
+    } else {
+        return warp_combine_unordered<Op>(st);
+    }
+}
+
+// parts == 1: warp per row.  parts == 8*S: one CTA per (row, s); its 8 warps take consecutive parts.
+template <class Op>
+__global__ void __launch_bounds__(kRedThreads) reduce_rows_kernel(const __grid_constant__ RedParams p, const Op op) {
+    using State = typename Op::State;
+    using Out = typename Op::Out;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (p.parts == 1) {
+        for (uint64_t r = (uint64_t)blockIdx.x * kRedWarps + warp; r < p.nrows; r += (uint64_t)gridDim.x * kRedWarps) {
+            int64_t soff, toff;
+            red_offsets(p.outer, (uint32_t)r, soff, toff);
+            State s = warp_fold_part<Op>(op, p.src + soff, 0, p.len, lane);
+            if (lane == 0) *reinterpret_cast<Out *>(p.dst + toff) = Op::finalize(s);
+        }
+        return;
+    }
+    __shared__ State sm[kRedWarps];
+    const uint64_t total = (uint64_t)p.nrows * p.ctas_per_row;
+    for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const uint32_t r = (uint32_t)(w / p.ctas_per_row);
+        const int s_idx = (int)(w % p.ctas_per_row);
+        int64_t soff, toff;
+        red_offsets(p.outer, r, soff, toff);
+        const int64_t part = (int64_t)s_idx * kRedWarps + warp;
+        int64_t b = part * p.part_len, e = b + p.part_len;
+        if (b > p.len) b = p.len;
+        if (e > p.len) e = p.len;
+        State s = warp_fold_part<Op>(op, p.src + soff, b, e, lane);
+        if (lane == 0) sm[warp] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            State acc = sm[0];
+#pragma unroll
+            for (int k = 1; k < kRedWarps; ++k) acc = Op::combine(acc, sm[k]);
+            if (p.ctas_per_row == 1) *reinterpret_cast<Out *>(p.dst + toff) = Op::finalize(acc);
+            else reinterpret_cast<State *>(p.partials)[(uint64_t)r * p.ctas_per_row + s_idx] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// Ordered combine of the per-CTA partial states of each row; one thread per row.
+template <class Op>
+__global__ void __launch_bounds__(kRedThreads) reduce_finalize_kernel(const __grid_constant__ RedParams p) {
+    using State = typename Op::State;
+    using Out = typename Op::Out;
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.nrows) return;
+    const State *part = reinterpret_cast<const State *>(p.partials) + r * p.ctas_per_row;
+    State acc = part[0];
+    for (int k = 1; k < p.ctas_per_row; ++k) acc = Op::combine(acc, part[k]);
+    int64_t soff, toff;
+    red_offsets(p.outer, (uint32_t)r, soff, toff);
+    *reinterpret_cast<Out *>(p.dst + toff) = Op::finalize(acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cols family: blockDim = (TX, TY); thread (x, y) folds chunk y of output x sequentially.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kColsTX = 32;
+
+template <class Op>
+__global__ void __launch_bounds__(kRedThreads) reduce_cols_kernel(const __grid_constant__ RedParams p, const Op op) {
+    using T = typename Op::In;
+    using State = typename Op::State;
+    using Out = typename Op::Out;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    State *sm = reinterpret_cast<State *>(smem_raw);  // [blockDim.y][blockDim.x]
+    const uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = blockIdx.y * blockDim.y + threadIdx.y;
+    State st = Op::identity();
+    int64_t soff = 0, toff = 0;
+    const bool active = o < p.nrows;
+    if (active) {
+        red_offsets(p.outer, (uint32_t)o, soff, toff);
+        int64_t b = (int64_t)chunk * p.part_len, e = b + p.part_len;
+        if (e > p.len) e = p.len;
+        const char *q = p.src + soff + b * p.lstride;
+        int64_t i = b;
+        for (; i + 4 <= e; i += 4) {
+            T v0 = *reinterpret_cast<const T *>(q);
+            T v1 = *reinterpret_cast<const T *>(q + p.lstride);
+            T v2 = *reinterpret_cast<const T *>(q + 2 * p.lstride);
+            T v3 = *reinterpret_cast<const T *>(q + 3 * p.lstride);
+            q += 4 * p.lstride;
+            op_step(op, st, v0, i);
+            op_step(op, st, v1, i + 1);
+            op_step(op, st, v2, i + 2);
+            op_step(op, st, v3, i + 3);
+        }
+        for (; i < e; ++i) {
+            op_step(op, st, *reinterpret_cast<const T *>(q), i);
+            q += p.lstride;
+        }
+    }
+    if (blockDim.y > 1) {
+        sm[threadIdx.y * blockDim.x + threadIdx.x] = st;
+        __syncthreads();
+        if (threadIdx.y != 0) return;
+        for (int y = 1; y < (int)blockDim.y; ++y) st = Op::combine(st, sm[y * blockDim.x + threadIdx.x]);
+    }
+    if (!active) return;
+    if (gridDim.y == 1) *reinterpret_cast<Out *>(p.dst + toff) = Op::finalize(st);
+    else reinterpret_cast<State *>(p.partials)[o * gridDim.y + blockIdx.y] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct RedPlan {
+    const char *src;
+    char *dst;
+    int64_t len, lstride_elems;
+    int nouter;
+    int64_t oshape[DN_MAX_DIMS], ostride_s[DN_MAX_DIMS], ostride_t[DN_MAX_DIMS];  // elements, innermost-first
+    int64_t nrows;
+    int in_size, out_size;
+};
+
+// Validates shapes (a: [..., L], t: [...]) and canonicalises the outer dims (drop size-1, sort by source stride,
+// merge). nrows == 0 means nothing to do.
+dn_status red_make_plan(RedPlan &plan, const dn_tensor *t, const dn_tensor *a, const char *what);
+void red_fill_outer(RedOuter &o, const RedPlan &plan);
+
+template <class Op>
+dn_status red_run(const RedPlan &plan, const Op &op) {
+    using State = typename Op::State;
+    using Out = typename Op::Out;
+    if (plan.nrows == 0) return DN_OK;
+    const int sms = sm_count();
+    const int64_t L = plan.len;
+    // rows family needs a contiguous reduced axis; tiny axes are better served by the cols family
+    const bool rows_family = (plan.lstride_elems == 1 || L <= 1) && L >= 64;
+    if (plan.nrows >= ((int64_t)1 << 31))
+        return set_error(DN_ERR_UNSUPPORTED, "reduction with more than 2^31-1 outputs is not supported");
+    {
+        const int64_t rc = plan.nrows;
+        RedParams p;
+        red_fill_outer(p.outer, plan);
+        p.src = plan.src;
+        p.dst = plan.dst;
+        p.nrows = (uint32_t)rc;
+        p.len = L;
+        p.lstride = plan.lstride_elems * plan.in_size;
+        p.partials = nullptr;
+        p.ctas_per_row = 1;
+        void *scratch = nullptr;
+        if (rows_family) {
+            const int64_t warps_wanted = (int64_t)sms * 32;  // enough resident warps to cover HBM latency
+            const int64_t bytes = L * plan.in_size;
+            if (rc >= warps_wanted / 4 || bytes <= 8192) {
+                p.parts = 1;
+                p.part_len = L;
+                int64_t ctas = (rc + kRedWarps - 1) / kRedWarps;
+                const int64_t cap = (int64_t)sms * 16;
+                if (ctas > cap) ctas = cap;
+                DN_LAUNCH((reduce_rows_kernel<Op>), (unsigned)ctas, kRedThreads, 0, p, op);
+            } else {
+                // S CTAs per row so that rc*S CTAs fill the machine; every part stays >= 4 KiB
+                int64_t S = (2 * (int64_t)sms + rc - 1) / rc;
+                const int64_t max_s = bytes / (kRedWarps * 4096);
+                if (S > max_s) S = max_s;
+                if (S < 1) S = 1;
+                if (S > 1024) S = 1024;
+                const int64_t nparts = S * kRedWarps;
+                constexpr int64_t kAlignElems = 512;  // keep part boundaries 16-byte aligned relative to the row
+                int64_t part_len = (L + nparts - 1) / nparts;
+                part_len = (part_len + kAlignElems - 1) / kAlignElems * kAlignElems;
+                p.parts = (int32_t)nparts;
+                p.part_len = part_len;
+                p.ctas_per_row = (int32_t)S;
+                if (S > 1) {
+                    dn_status st = scratch_alloc((size_t)rc * S * sizeof(State), &scratch);
+                    if (st != DN_OK) return st;
+                    p.partials = scratch;
+                }
+                int64_t ctas = rc * S;
+                const int64_t cap = (int64_t)sms * 16;
+                if (ctas > cap) ctas = cap;
+                DN_LAUNCH((reduce_rows_kernel<Op>), (unsigned)ctas, kRedThreads, 0, p, op);
+                if (S > 1) {
+                    DN_LAUNCH((reduce_finalize_kernel<Op>), (unsigned)((rc + kRedThreads - 1) / kRedThreads),
+                              kRedThreads, 0, p);
+                }
+            }
+        } else {
+            // cols family: TX threads along outputs; TY*GY chunks along the axis when outputs alone cannot fill
+            // the machine.
+            int tx = kColsTX, ty = kRedThreads / kColsTX;
+            int64_t gx = (rc + tx - 1) / tx;
+            int64_t gy = 1;
+            if (L < 64) {  // short axis: no point in splitting it
+                tx = kRedThreads;
+                ty = 1;
+                gx = (rc + tx - 1) / tx;
+            } else if (gx < 2 * sms) {
+                gy = (2 * (int64_t)sms + gx - 1) / gx;
+                const int64_t max_gy = L / (ty * 64) > 0 ? L / (ty * 64) : 1;
+                if (gy > max_gy) gy = max_gy;
+                if (gy > 65535) gy = 65535;
+            }
+            const int64_t chunks = (int64_t)ty * gy;
+            p.parts = (int32_t)chunks;
+            p.part_len = (L + chunks - 1) / chunks;
+            if (p.part_len < 1) p.part_len = 1;
+            p.ctas_per_row = (int32_t)gy;
+            if (gy > 1) {
+                dn_status st = scratch_alloc((size_t)rc * gy * sizeof(State), &scratch);
+                if (st != DN_OK) return st;
+                p.partials = scratch;
+            }
+            const size_t smem = ty > 1 ? (size_t)tx * ty * sizeof(State) : 0;
+            DN_LAUNCH((reduce_cols_kernel<Op>), dim3((unsigned)gx, (unsigned)gy), dim3(tx, ty), smem, p, op);
+            if (gy > 1) {
+                DN_LAUNCH((reduce_finalize_kernel<Op>), (unsigned)((rc + kRedThreads - 1) / kRedThreads),
+                          kRedThreads, 0, p);
+            }
+        }
+        scratch_free(scratch);
+        (void)sizeof(Out);
+    }
+    return launch_status("reduction kernel");
+}
+
+}  // namespace dn

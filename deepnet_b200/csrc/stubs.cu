@@ -2,9 +2,6 @@
 #include "common.cuh"
 using namespace dn;
 extern "C" {
-dn_status dn_reduce_last_axis(int32_t, const dn_tensor *, const dn_tensor *) { return set_error(DN_ERR_UNSUPPORTED, "nyi"); }
-dn_status dn_arg_reduce_last_axis(int32_t, const dn_tensor *, const dn_tensor *) { return set_error(DN_ERR_UNSUPPORTED, "nyi"); }
-dn_status dn_find_last_axis(const void *, const dn_tensor *, const dn_tensor *) { return set_error(DN_ERR_UNSUPPORTED, "nyi"); }
 dn_status dn_gather(const dn_tensor *, const dn_tensor *const *, int32_t, const dn_tensor *) { return set_error(DN_ERR_UNSUPPORTED, "nyi"); }
 dn_status dn_scatter(const dn_tensor *, const dn_tensor *const *, int32_t, const dn_tensor *) { return set_error(DN_ERR_UNSUPPORTED, "nyi"); }
 dn_status dn_count_true(const dn_tensor *, int64_t *) { return set_error(DN_ERR_UNSUPPORTED, "nyi"); }
@@ -15,5 +12,4 @@ dn_status dn_vec_vec_dot(const dn_tensor *, const dn_tensor *, const dn_tensor *
 dn_status dn_mat_vec_dot(const dn_tensor *, const dn_tensor *, const dn_tensor *) { return set_error(DN_ERR_UNSUPPORTED, "nyi"); }
 dn_status dn_mat_mat_dot(const dn_tensor *, const dn_tensor *, const dn_tensor *) { return set_error(DN_ERR_UNSUPPORTED, "nyi"); }
 dn_status dn_batched_mat_mat_dot(const dn_tensor *, const dn_tensor *, const dn_tensor *) { return set_error(DN_ERR_UNSUPPORTED, "nyi"); }
-dn_status dn_arg_reduce_combine(int32_t, const dn_tensor *, const dn_tensor *, const dn_tensor *) { return set_error(DN_ERR_UNSUPPORTED, "nyi"); }
 }
