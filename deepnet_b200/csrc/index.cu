@@ -1,0 +1,692 @@
+// index.cu — Gather, Scatter, CountTrue, MaskedGet, MaskedSet, TrueIndices (Tensor/Tensor/TensorBackend.fs:119-123).
+//
+// Gather / Scatter replace CudaBackend.fs:362-381, CudaKernels.fs:302-345 and Kernels/GatherScatter.cuh:26-114.
+// MaskedGet / MaskedSet / TrueIndices / CountTrue do not exist in the reference's CUDA backend at all
+// (CudaBackend.fs:489-492 raise NotSupportedException); their semantics are the host's (ScalarOps.fs:667-707):
+// walk the tensor in LOGICAL row-major order of the view, whatever its strides.
+//
+// Ordered compaction: one primitive shared by TrueIndices, MaskedGet and MaskedSet —
+//   pass 1  every CTA counts the true elements of its tile of 4096 consecutive logical positions
+//           (thread = 16 consecutive positions, one 128-bit load when they are contiguous in memory);
+//   scan    exclusive scan of the per-tile counts (one CTA, they are only N/4096 values);
+//   pass 2  every CTA re-reads its tile (L2-resident for typical masks), ranks its true elements with a
+//           ballot-free register count + warp shuffle scan, and hands (rank, logical position) to a sink:
+//           coordinates (TrueIndices), source -> dense target (MaskedGet), dense values -> target (MaskedSet),
+//           or a plain index list (per-dimension masks, which select a cartesian product: ScalarOps.fs:672-681).
+#include "ew_ops.cuh"
+
+using namespace dn;
+
+namespace {
+
+constexpr int kIdxThreads = 256;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gather / Scatter
+// ---------------------------------------------------------------------------------------------------------------
+struct GSParams {
+    char *it_ptr;       // tensor that is walked: target (gather) / source (scatter)
+    char *other_ptr;    // tensor that is indexed: source (gather) / target (scatter)
+    int32_t nd_it, nd_other;
+    uint32_t n;
+    uint32_t it_shape[DN_MAX_DIMS];     // innermost-first
+    FastDiv it_div[DN_MAX_DIMS];
+    int64_t it_stride[DN_MAX_DIMS];     // bytes, innermost-first
+    int64_t other_shape[DN_MAX_DIMS];   // descriptor order
+    int64_t other_stride[DN_MAX_DIMS];  // bytes, descriptor order
+    const char *idx_ptr[DN_MAX_DIMS];   // per indexed dim (descriptor order), nullptr = None
+    int64_t idx_stride[DN_MAX_DIMS][DN_MAX_DIMS];  // bytes, [indexed dim][walked dim innermost-first]
+    int *err;
+};
+
+// Decomposes walked position `f` into the byte offset into the walked tensor and the byte offset into the indexed
+// tensor; returns false if an index is out of range.
+__device__ __forceinline__ bool gs_addresses(const GSParams &p, uint32_t f, int64_t &it_off, int64_t &other_off) {
+    uint32_t pos[DN_MAX_DIMS];
+    uint32_t rem = f;
+    it_off = 0;
+#pragma unroll
+    for (int k = 0; k < DN_MAX_DIMS; ++k) {
+        if (k >= p.nd_it) break;
+        uint32_t q, x;
+        if (k == p.nd_it - 1) { x = rem; q = 0; }
+        else { q = p.it_div[k].div(rem); x = rem - q * p.it_shape[k]; }
+        pos[k] = x;
+        it_off += (int64_t)x * p.it_stride[k];
+        rem = q;
+    }
+    other_off = 0;
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < DN_MAX_DIMS; ++d) {
+        if (d >= p.nd_other) break;
+        int64_t ix;
+        if (p.idx_ptr[d]) {
+            int64_t io = 0;
+#pragma unroll
+            for (int k = 0; k < DN_MAX_DIMS; ++k) {
+                if (k >= p.nd_it) break;
+                io += (int64_t)pos[k] * p.idx_stride[d][k];
+            }
+            ix = *reinterpret_cast<const int64_t *>(p.idx_ptr[d] + io);
+        } else {
+            ix = 0;  // None: identity on descriptor dim d (walked dim nd_it-1-d, innermost-first)
+#pragma unroll
+            for (int k = 0; k < DN_MAX_DIMS; ++k)
+                if (k == p.nd_it - 1 - d) ix = pos[k];
+        }
+        ok = ok && ix >= 0 && ix < p.other_shape[d];
+        other_off += ix * p.other_stride[d];
+    }
+    return ok;
+}
+
+template <class B>
+__global__ void __launch_bounds__(kIdxThreads) gather_kernel(const __grid_constant__ GSParams p) {
+    constexpr int U = 4;
+    for (uint64_t base = (uint64_t)blockIdx.x * (kIdxThreads * U); base < p.n; base += (uint64_t)gridDim.x * (kIdxThreads * U)) {
+        int64_t to[U], so[U];
+        int state[U];  // 0 = inactive, 1 = in range, 2 = index out of range
+        B v[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint64_t f = base + (uint32_t)j * kIdxThreads + threadIdx.x;
+            state[j] = 0;
+            if (f < p.n) state[j] = gs_addresses(p, (uint32_t)f, to[j], so[j]) ? 1 : 2;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+            if (state[j] == 1) v[j] = *reinterpret_cast<const B *>(p.other_ptr + so[j]);
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (state[j] == 1) *reinterpret_cast<B *>(p.it_ptr + to[j]) = v[j];
+            else if (state[j] == 2) atomicExch(p.err, 1);
+        }
+    }
+}
+
+// atomic add for every numeric element type (Scatter sums duplicates; GatherScatter.cuh:89 uses atomicAdd, which
+// has no int64 / 16-bit / 8-bit overloads — those go through unsigned wrap-around or a CAS on the enclosing word).
+template <class T> __device__ __forceinline__ void atomic_add_any(T *addr, T v) {
+    if constexpr (std::is_same<T, float>::value || std::is_same<T, double>::value ||
+                  std::is_same<T, int32_t>::value || std::is_same<T, uint32_t>::value) {
+        atomicAdd(addr, v);
+    } else if constexpr (sizeof(T) == 8) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)v);
+    } else {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(addr);
+        unsigned *word = reinterpret_cast<unsigned *>(a & ~(uintptr_t)3);
+        const unsigned shift = (unsigned)(a & 3) * 8;
+        const unsigned mask = (sizeof(T) == 1 ? 0xffu : 0xffffu) << shift;
+        unsigned old = *word, assumed;
+        do {
+            assumed = old;
+            const unsigned cur = (assumed & mask) >> shift;
+            const unsigned sum = (cur + (unsigned)(typename std::make_unsigned<T>::type)v) << shift;
+            old = atomicCAS(word, assumed, (assumed & ~mask) | (sum & mask));
+        } while (old != assumed);
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kIdxThreads) scatter_kernel(const __grid_constant__ GSParams p) {
+    constexpr int U = 4;
+    for (uint64_t base = (uint64_t)blockIdx.x * (kIdxThreads * U); base < p.n; base += (uint64_t)gridDim.x * (kIdxThreads * U)) {
+        int64_t so[U], to[U];
+        int state[U];
+        T v[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint64_t f = base + (uint32_t)j * kIdxThreads + threadIdx.x;
+            state[j] = 0;
+            if (f < p.n) {
+                state[j] = gs_addresses(p, (uint32_t)f, so[j], to[j]) ? 1 : 2;
+                v[j] = *reinterpret_cast<const T *>(p.it_ptr + so[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (state[j] == 1) atomic_add_any(reinterpret_cast<T *>(p.other_ptr + to[j]), v[j]);
+            else if (state[j] == 2) atomicExch(p.err, 1);
+        }
+    }
+}
+
+dn_status gs_fill(GSParams &p, const dn_tensor *walked, const dn_tensor *other, const dn_tensor *const *idxs,
+                  const char *what) {
+    const int64_t n = num_elements(walked);
+    if (n >= ((int64_t)1 << 31)) return set_error(DN_ERR_UNSUPPORTED, "%s: more than 2^31-1 elements", what);
+    p.n = (uint32_t)n;
+    p.it_ptr = data_ptr(walked);
+    p.other_ptr = data_ptr(other);
+    p.nd_it = walked->ndims;
+    p.nd_other = other->ndims;
+    const int wsz = dtype_size(walked->dtype), osz = dtype_size(other->dtype);
+    for (int k = 0; k < DN_MAX_DIMS; ++k) {
+        const int d = walked->ndims - 1 - k;
+        p.it_shape[k] = d >= 0 ? (uint32_t)walked->shape[d] : 1;
+        p.it_div[k].init(p.it_shape[k]);
+        p.it_stride[k] = d >= 0 ? walked->stride[d] * wsz : 0;
+    }
+    for (int d = 0; d < DN_MAX_DIMS; ++d) {
+        const bool on = d < other->ndims;
+        p.other_shape[d] = on ? other->shape[d] : 1;
+        p.other_stride[d] = on ? other->stride[d] * osz : 0;
+        p.idx_ptr[d] = (on && idxs[d]) ? data_ptr(idxs[d]) : nullptr;
+        for (int k = 0; k < DN_MAX_DIMS; ++k) {
+            const int wd = walked->ndims - 1 - k;
+            p.idx_stride[d][k] = (on && idxs[d] && wd >= 0) ? idxs[d]->stride[wd] * 8 : 0;
+        }
+    }
+    p.err = index_error_flag();
+    if (!p.err) return set_error(DN_ERR_NO_DEVICE, "%s: device not initialised (call dn_init)", what);
+    return DN_OK;
+}
+
+dn_status check_index_error(const char *what) {
+    if (!check_errors_enabled()) return DN_OK;
+    int h = 0;
+    DN_CUDA_TRY(cudaMemcpyAsync(&h, index_error_flag(), sizeof(int), cudaMemcpyDeviceToHost, current_stream()));
+    DN_CUDA_TRY(cudaStreamSynchronize(current_stream()));
+    if (h) {
+        DN_CUDA_TRY(cudaMemsetAsync(index_error_flag(), 0, sizeof(int), current_stream()));
+        return set_error(DN_ERR_INDEX_OUT_OF_RANGE, "invalid index during gather or scatter (%s)", what);
+    }
+    return DN_OK;
+}
+
+dn_status validate_gs(const dn_tensor *walked, const dn_tensor *other, const dn_tensor *const *idxs, int nidxs,
+                      const char *what) {
+    if (!tensor_valid(walked) || !tensor_valid(other) || !idxs)
+        return set_error(DN_ERR_INVALID_ARG, "%s: bad argument", what);
+    if (walked->dtype != other->dtype) return set_error(DN_ERR_INVALID_ARG, "%s: source and target types differ", what);
+    if (nidxs != other->ndims)
+        return set_error(DN_ERR_INVALID_ARG, "%s: one index tensor (or None) per indexed dimension is required", what);
+    for (int d = 0; d < nidxs; ++d) {
+        if (idxs[d]) {
+            if (!tensor_valid(idxs[d]) || idxs[d]->dtype != DN_I64 || !same_shape(idxs[d], walked))
+                return set_error(DN_ERR_INVALID_ARG, "%s: index tensors must be int64 and have the walked tensor's shape", what);
+        } else if (d >= walked->ndims) {
+            return set_error(DN_ERR_INVALID_ARG, "%s: index dimensions beyond the walked tensor's rank must not be None", what);
+        }
+    }
+    return DN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ordered compaction
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kItems = 16;                          // consecutive logical positions per thread
+constexpr int kTileElems = kIdxThreads * kItems;    // 4096 per CTA
+
+struct BoolView {           // a bool tensor walked in logical row-major order
+    const char *ptr;
+    int32_t nd;
+    uint32_t n;
+    uint32_t shape[DN_MAX_DIMS];   // innermost-first
+    FastDiv div[DN_MAX_DIMS];
+    int64_t stride[DN_MAX_DIMS];   // bytes
+};
+
+// Loads the (up to 16) mask bytes of logical positions [f0, f0+16) into bits of a 16-bit word.
+__device__ __forceinline__ uint32_t load_mask_bits(const BoolView &m, uint32_t f0) {
+    if (f0 >= m.n) return 0;
+    uint32_t pos[DN_MAX_DIMS];
+    uint32_t rem = f0;
+    int64_t off = 0;
+#pragma unroll
+    for (int k = 0; k < DN_MAX_DIMS; ++k) {
+        if (k >= m.nd) break;
+        uint32_t q, x;
+        if (k == m.nd - 1) { x = rem; q = 0; }
+        else { q = m.div[k].div(rem); x = rem - q * m.shape[k]; }
+        pos[k] = x;
+        off += (int64_t)x * m.stride[k];
+        rem = q;
+    }
+    const uint32_t cnt = (m.n - f0 < (uint32_t)kItems) ? m.n - f0 : (uint32_t)kItems;
+    const char *a = m.ptr + off;
+    uint32_t bits = 0;
+    if (cnt == kItems && m.stride[0] == 1 && pos[0] + kItems <= m.shape[0] && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(a);
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t nz = __vcmpne4(ws[i], 0u);  // 0xff per non-zero byte
+            bits |= ((nz & 1u) | ((nz >> 7) & 2u) | ((nz >> 14) & 4u) | ((nz >> 21) & 8u)) << (4 * i);
+        }
+        return bits;
+    }
+    // generic: odometer walk
+    for (uint32_t j = 0; j < cnt; ++j) {
+        if (*reinterpret_cast<const uint8_t *>(m.ptr + off)) bits |= 1u << j;
+        // advance one logical position
+#pragma unroll
+        for (int k = 0; k < DN_MAX_DIMS; ++k) {
+            if (k >= m.nd) break;
+            off += m.stride[k];
+            if (++pos[k] < m.shape[k] || k == m.nd - 1) break;
+            off -= (int64_t)m.shape[k] * m.stride[k];
+            pos[k] = 0;
+        }
+    }
+    return bits;
+}
+
+__global__ void __launch_bounds__(kIdxThreads) mask_count_kernel(const __grid_constant__ BoolView m, uint32_t *tile_counts,
+                                                              unsigned long long *total) {
+    __shared__ uint32_t warp_sums[kIdxThreads / 32];
+    for (uint32_t tile = blockIdx.x; (uint64_t)tile * kTileElems < m.n; tile += gridDim.x) {
+        const uint32_t f0 = tile * kTileElems + threadIdx.x * kItems;
+        uint32_t c = __popc(load_mask_bits(m, f0));
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+        if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < kIdxThreads / 32; ++w) t += warp_sums[w];
+            if (tile_counts) tile_counts[tile] = t;
+            if (total && t) atomicAdd(total, (unsigned long long)t);
+        }
+        __syncthreads();
+    }
+}
+
+// Exclusive scan of tile counts -> int64 offsets (single CTA; ntiles = N / 4096 is small).
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t *counts, int64_t *offsets, uint32_t ntiles) {
+    __shared__ int64_t warp_tot[32];
+    __shared__ int64_t warp_excl[32];
+    __shared__ int64_t chunk_total;
+    __shared__ int64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < ntiles; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const int64_t v = i < ntiles ? (int64_t)counts[i] : 0;
+        int64_t incl = v;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int64_t o = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += o;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int64_t w = warp_tot[lane];
+            int64_t wi = w;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int64_t o = __shfl_up_sync(0xffffffffu, wi, s);
+                if (lane >= s) wi += o;
+            }
+            warp_excl[lane] = wi - w;
+            if (lane == 31) chunk_total = wi;
+        }
+        __syncthreads();
+        if (i < ntiles) offsets[i] = carry_s + warp_excl[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += chunk_total;
+        __syncthreads();
+    }
+}
+
+// Sinks --------------------------------------------------------------------------------------------------------
+struct CoordSink {  // TrueIndices: t[rank, d] = coordinate d of the element (descriptor dim order)
+    char *t;
+    int64_t ts0, ts1;  // bytes
+    int64_t cap;       // rows available in t
+    int32_t nd;
+    uint32_t shape[DN_MAX_DIMS];  // innermost-first (same as the BoolView)
+    FastDiv div[DN_MAX_DIMS];
+    __device__ __forceinline__ void operator()(int64_t rank, uint32_t f) const {
+        if (rank >= cap) return;
+        uint32_t rem = f;
+#pragma unroll
+        for (int k = 0; k < DN_MAX_DIMS; ++k) {
+            if (k >= nd) break;
+            uint32_t q, x;
+            if (k == nd - 1) { x = rem; q = 0; }
+            else { q = div[k].div(rem); x = rem - q * shape[k]; }
+            *reinterpret_cast<int64_t *>(t + rank * ts0 + (int64_t)(nd - 1 - k) * ts1) = (int64_t)x;
+            rem = q;
+        }
+    }
+};
+
+struct IndexListSink {  // sel[rank] = f
+    int64_t *sel;
+    int64_t cap;
+    __device__ __forceinline__ void operator()(int64_t rank, uint32_t f) const {
+        if (rank < cap) sel[rank] = (int64_t)f;
+    }
+};
+
+template <class B>
+struct GetSink {  // MaskedGet 1-D: t[rank] = a[f]
+    char *t;
+    const char *a;
+    int64_t ts, as;  // bytes
+    int64_t cap;
+    __device__ __forceinline__ void operator()(int64_t rank, uint32_t f) const {
+        if (rank < cap) *reinterpret_cast<B *>(t + rank * ts) = *reinterpret_cast<const B *>(a + (int64_t)f * as);
+    }
+};
+
+template <class B>
+struct SetSink {  // MaskedSet 1-D: t[f] = a[rank]
+    char *t;
+    const char *a;
+    int64_t ts, as;
+    int64_t cap;  // values available in a
+    __device__ __forceinline__ void operator()(int64_t rank, uint32_t f) const {
+        if (rank < cap) *reinterpret_cast<B *>(t + (int64_t)f * ts) = *reinterpret_cast<const B *>(a + rank * as);
+    }
+};
+
+template <class Sink>
+__global__ void __launch_bounds__(kIdxThreads) mask_emit_kernel(const __grid_constant__ BoolView m, const int64_t *tile_offsets,
+                                                             const Sink sink) {
+    __shared__ uint32_t warp_sums[kIdxThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x; (uint64_t)tile * kTileElems < m.n; tile += gridDim.x) {
+        const uint32_t f0 = tile * kTileElems + threadIdx.x * kItems;
+        const uint32_t bits = load_mask_bits(m, f0);
+        const uint32_t c = __popc(bits);
+        uint32_t incl = c;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += o;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < kIdxThreads / 32; ++w)
+            if (w < warp) before += warp_sums[w];
+        int64_t rank = tile_offsets[tile] + before + incl - c;
+        uint32_t b = bits;
+        while (b) {
+            const int j = __ffs(b) - 1;
+            b &= b - 1;
+            sink(rank++, f0 + j);
+        }
+        __syncthreads();
+    }
+}
+
+dn_status make_bool_view(BoolView &v, const dn_tensor *a, const char *what) {
+    const int64_t n = num_elements(a);
+    if (n >= ((int64_t)1 << 31)) return set_error(DN_ERR_UNSUPPORTED, "%s: more than 2^31-1 elements", what);
+    v.ptr = data_ptr(a);
+    v.nd = a->ndims;
+    v.n = (uint32_t)n;
+    for (int k = 0; k < DN_MAX_DIMS; ++k) {
+        const int d = a->ndims - 1 - k;
+        v.shape[k] = d >= 0 ? (uint32_t)a->shape[d] : 1;
+        v.div[k].init(v.shape[k]);
+        v.stride[k] = d >= 0 ? a->stride[d] : 0;
+    }
+    if (v.nd == 0) {  // rank 0: one element
+        v.nd = 1;
+        v.shape[0] = 1;
+        v.div[0].init(1);
+        v.stride[0] = 0;
+    }
+    return DN_OK;
+}
+
+int tiles_grid(uint32_t ntiles) {
+    const int64_t cap = (int64_t)sm_count() * 16;
+    return (int)(ntiles < cap ? (ntiles ? ntiles : 1) : cap);
+}
+
+// Runs count + scan + emit for one bool view.
+template <class Sink>
+dn_status run_compaction(const BoolView &m, const Sink &sink) {
+    if (m.n == 0) return DN_OK;
+    const uint32_t ntiles = (uint32_t)(((uint64_t)m.n + kTileElems - 1) / kTileElems);
+    void *scratch = nullptr;
+    dn_status st = scratch_alloc((size_t)ntiles * (sizeof(uint32_t) + sizeof(int64_t)) + 16, &scratch);
+    if (st != DN_OK) return st;
+    int64_t *offsets = reinterpret_cast<int64_t *>(scratch);
+    uint32_t *counts = reinterpret_cast<uint32_t *>(offsets + ntiles);
+    DN_LAUNCH(mask_count_kernel, tiles_grid(ntiles), kIdxThreads, 0, m, counts, (unsigned long long *)nullptr);
+    DN_LAUNCH(tile_scan_kernel, 1, 1024, 0, counts, offsets, ntiles);
+    DN_LAUNCH((mask_emit_kernel<Sink>), tiles_grid(ntiles), kIdxThreads, 0, m, offsets, sink);
+    scratch_free(scratch);
+    return launch_status("compaction kernels");
+}
+
+// Separable gather / scatter through per-dimension index lists (general MaskedGet / MaskedSet).
+struct SepParams {
+    char *dense;          // the dense side: MaskedGet target / MaskedSet values
+    char *full;           // the full side: MaskedGet source / MaskedSet target
+    int32_t nd;
+    uint32_t n;           // elements of the dense side
+    uint32_t dshape[DN_MAX_DIMS];   // dense shape, innermost-first
+    FastDiv ddiv[DN_MAX_DIMS];
+    int64_t dstride[DN_MAX_DIMS];   // bytes
+    int64_t fstride[DN_MAX_DIMS];   // bytes
+    const int64_t *sel[DN_MAX_DIMS];  // per dim index list or nullptr (identity)
+};
+
+template <class B, bool IsGet>
+__global__ void __launch_bounds__(kIdxThreads) separable_kernel(const __grid_constant__ SepParams p) {
+    for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < p.n; f += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t rem = (uint32_t)f;
+        int64_t doff = 0, foff = 0;
+#pragma unroll
+        for (int k = 0; k < DN_MAX_DIMS; ++k) {
+            if (k >= p.nd) break;
+            uint32_t q, x;
+            if (k == p.nd - 1) { x = rem; q = 0; }
+            else { q = p.ddiv[k].div(rem); x = rem - q * p.dshape[k]; }
+            doff += (int64_t)x * p.dstride[k];
+            const int64_t fx = p.sel[k] ? p.sel[k][x] : (int64_t)x;
+            foff += fx * p.fstride[k];
+            rem = q;
+        }
+        if (IsGet) *reinterpret_cast<B *>(p.dense + doff) = *reinterpret_cast<const B *>(p.full + foff);
+        else *reinterpret_cast<B *>(p.full + foff) = *reinterpret_cast<const B *>(p.dense + doff);
+    }
+}
+
+dn_status check_masks(const dn_tensor *full, const dn_tensor *dense, const dn_tensor *const *masks, int nmasks,
+                      const char *what) {
+    if (!tensor_valid(full) || !tensor_valid(dense) || !masks)
+        return set_error(DN_ERR_INVALID_ARG, "%s: bad argument", what);
+    if (full->dtype != dense->dtype || full->ndims != dense->ndims)
+        return set_error(DN_ERR_INVALID_ARG, "%s: source and target must have the same type and rank", what);
+    if (nmasks != full->ndims)
+        return set_error(DN_ERR_INVALID_ARG, "%s: one mask (or NoMask) per dimension is required", what);
+    for (int d = 0; d < nmasks; ++d) {
+        if (masks[d]) {
+            if (!tensor_valid(masks[d]) || masks[d]->dtype != DN_BOOL || masks[d]->ndims != 1 ||
+                masks[d]->shape[0] != full->shape[d])
+                return set_error(DN_ERR_INVALID_ARG, "%s: mask %d must be a 1-D bool tensor of length %lld", what, d,
+                                 (long long)full->shape[d]);
+        } else if (dense->shape[d] != full->shape[d]) {
+            return set_error(DN_ERR_SHAPE_MISMATCH, "%s: unmasked dimension %d must have equal sizes", what, d);
+        }
+    }
+    return DN_OK;
+}
+
+template <bool IsGet>
+dn_status masked_general(const dn_tensor *dense, const dn_tensor *full, const dn_tensor *const *masks, const char *what) {
+    const int nd = full->ndims;
+    const int64_t n = num_elements(dense);
+    if (n == 0) return DN_OK;
+    if (n >= ((int64_t)1 << 31)) return set_error(DN_ERR_UNSUPPORTED, "%s: more than 2^31-1 elements", what);
+    // index lists for the masked dims, in one scratch block
+    int64_t total = 0;
+    for (int d = 0; d < nd; ++d)
+        if (masks[d]) total += dense->shape[d];
+    void *scratch = nullptr;
+    dn_status st = scratch_alloc((size_t)(total + 1) * sizeof(int64_t), &scratch);
+    if (st != DN_OK) return st;
+    // zero the lists so that a target larger than the number of selected elements reads index 0, never garbage
+    cudaMemsetAsync(scratch, 0, (size_t)(total + 1) * sizeof(int64_t), current_stream());
+    SepParams p;
+    int64_t *cursor = reinterpret_cast<int64_t *>(scratch);
+    const int sz = dtype_size(full->dtype);
+    p.nd = nd;
+    p.n = (uint32_t)n;
+    p.dense = data_ptr(dense);
+    p.full = data_ptr(full);
+    for (int k = 0; k < DN_MAX_DIMS; ++k) {
+        const int d = nd - 1 - k;
+        p.dshape[k] = d >= 0 ? (uint32_t)dense->shape[d] : 1;
+        p.ddiv[k].init(p.dshape[k]);
+        p.dstride[k] = d >= 0 ? dense->stride[d] * sz : 0;
+        p.fstride[k] = d >= 0 ? full->stride[d] * sz : 0;
+        p.sel[k] = nullptr;
+        if (d >= 0 && masks[d]) {
+            BoolView mv;
+            st = make_bool_view(mv, masks[d], what);
+            if (st == DN_OK) st = run_compaction(mv, IndexListSink{cursor, dense->shape[d]});
+            if (st != DN_OK) {
+                scratch_free(scratch);
+                return st;
+            }
+            p.sel[k] = cursor;
+            cursor += dense->shape[d];
+        }
+    }
+    const int grid = ew_grid_for(n, kIdxThreads);
+    DN_SWITCH_SIZE(sz, { DN_LAUNCH((separable_kernel<B, IsGet>), grid, kIdxThreads, 0, p); });
+    scratch_free(scratch);
+    return launch_status(what);
+}
+
+}  // namespace
+
+extern "C" {
+
+dn_status dn_gather(const dn_tensor *t, const dn_tensor *const *idxs, int32_t nidxs, const dn_tensor *a) {
+    dn_status st = validate_gs(t, a, idxs, nidxs, "Gather");
+    if (st != DN_OK) return st;
+    if (num_elements(t) == 0) return DN_OK;
+    GSParams p;
+    st = gs_fill(p, t, a, idxs, "Gather");
+    if (st != DN_OK) return st;
+    const int grid = ew_grid_for(p.n, kIdxThreads * 4);
+    DN_SWITCH_SIZE(dtype_size(t->dtype), { DN_LAUNCH((gather_kernel<B>), grid, kIdxThreads, 0, p); });
+    st = launch_status("gather kernel");
+    if (st != DN_OK) return st;
+    return check_index_error("Gather");
+}
+
+dn_status dn_scatter(const dn_tensor *t, const dn_tensor *const *idxs, int32_t nidxs, const dn_tensor *a) {
+    dn_status st = validate_gs(a, t, idxs, nidxs, "Scatter");
+    if (st != DN_OK) return st;
+    if (t->dtype == DN_BOOL) return set_error(DN_ERR_UNSUPPORTED, "Scatter is not defined for type bool (no addition)");
+    // zero-fill (CudaBackend.fs:379), then accumulate
+    uint64_t zero = 0;
+    st = dn_fill_const(t, &zero);
+    if (st != DN_OK) return st;
+    if (num_elements(a) == 0) return DN_OK;
+    GSParams p;
+    st = gs_fill(p, a, t, idxs, "Scatter");
+    if (st != DN_OK) return st;
+    const int grid = ew_grid_for(p.n, kIdxThreads * 4);
+    switch (t->dtype) {
+    case DN_F32: DN_LAUNCH((scatter_kernel<float>), grid, kIdxThreads, 0, p); break;
+    case DN_F64: DN_LAUNCH((scatter_kernel<double>), grid, kIdxThreads, 0, p); break;
+    case DN_I8: DN_LAUNCH((scatter_kernel<int8_t>), grid, kIdxThreads, 0, p); break;
+    case DN_U8: DN_LAUNCH((scatter_kernel<uint8_t>), grid, kIdxThreads, 0, p); break;
+    case DN_I16: DN_LAUNCH((scatter_kernel<int16_t>), grid, kIdxThreads, 0, p); break;
+    case DN_U16: DN_LAUNCH((scatter_kernel<uint16_t>), grid, kIdxThreads, 0, p); break;
+    case DN_I32: DN_LAUNCH((scatter_kernel<int32_t>), grid, kIdxThreads, 0, p); break;
+    case DN_U32: DN_LAUNCH((scatter_kernel<uint32_t>), grid, kIdxThreads, 0, p); break;
+    case DN_I64: DN_LAUNCH((scatter_kernel<int64_t>), grid, kIdxThreads, 0, p); break;
+    case DN_U64: DN_LAUNCH((scatter_kernel<uint64_t>), grid, kIdxThreads, 0, p); break;
+    default: return set_error(DN_ERR_INVALID_ARG, "bad dtype");
+    }
+    st = launch_status("scatter kernel");
+    if (st != DN_OK) return st;
+    return check_index_error("Scatter");
+}
+
+dn_status dn_count_true(const dn_tensor *a, int64_t *count) {
+    if (!tensor_valid(a) || !count || a->dtype != DN_BOOL) return set_error(DN_ERR_INVALID_ARG, "countTrue: bad argument");
+    *count = 0;
+    BoolView m;
+    dn_status st = make_bool_view(m, a, "countTrue");
+    if (st != DN_OK) return st;
+    if (m.n == 0) return DN_OK;
+    void *scratch = nullptr;
+    st = scratch_alloc(sizeof(unsigned long long), &scratch);
+    if (st != DN_OK) return st;
+    DN_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), current_stream()));
+    const uint32_t ntiles = (uint32_t)(((uint64_t)m.n + kTileElems - 1) / kTileElems);
+    DN_LAUNCH(mask_count_kernel, tiles_grid(ntiles), kIdxThreads, 0, m, (uint32_t *)nullptr, (unsigned long long *)scratch);
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, scratch, sizeof h, cudaMemcpyDeviceToHost, current_stream());
+    if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());
+    scratch_free(scratch);
+    if (e != cudaSuccess) return cuda_error(e, "countTrue");
+    *count = (int64_t)h;
+    return DN_OK;
+}
+
+dn_status dn_true_indices(const dn_tensor *t, const dn_tensor *a) {
+    if (!tensor_valid(t) || !tensor_valid(a)) return set_error(DN_ERR_INVALID_ARG, "TrueIndices: bad argument");
+    if (t->dtype != DN_I64 || a->dtype != DN_BOOL || t->ndims != 2 || t->shape[1] != a->ndims)
+        return set_error(DN_ERR_INVALID_ARG, "TrueIndices: target must be int64 of shape [nTrue, %d]", a->ndims);
+    if (t->shape[0] == 0 || a->ndims == 0) return DN_OK;
+    BoolView m;
+    dn_status st = make_bool_view(m, a, "TrueIndices");
+    if (st != DN_OK) return st;
+    CoordSink sink;
+    sink.t = data_ptr(t);
+    sink.ts0 = t->stride[0] * 8;
+    sink.ts1 = t->stride[1] * 8;
+    sink.cap = t->shape[0];
+    sink.nd = m.nd;
+    for (int k = 0; k < DN_MAX_DIMS; ++k) {
+        sink.shape[k] = m.shape[k];
+        sink.div[k] = m.div[k];
+    }
+    return run_compaction(m, sink);
+}
+
+dn_status dn_masked_get(const dn_tensor *t, const dn_tensor *a, const dn_tensor *const *masks, int32_t nmasks) {
+    dn_status st = check_masks(a, t, masks, nmasks, "MaskedGet");
+    if (st != DN_OK) return st;
+    if (num_elements(t) == 0) return DN_OK;
+    if (a->ndims == 1 && masks[0]) {  // one mask over a flattened tensor: fused compaction
+        BoolView m;
+        st = make_bool_view(m, masks[0], "MaskedGet");
+        if (st != DN_OK) return st;
+        const int sz = dtype_size(a->dtype);
+        DN_SWITCH_SIZE(sz, {
+            GetSink<B> sink{data_ptr(t), data_ptr(a), t->stride[0] * sz, a->stride[0] * sz, t->shape[0]};
+            return run_compaction(m, sink);
+        });
+    }
+    return masked_general<true>(t, a, masks, "MaskedGet");
+}
+
+dn_status dn_masked_set(const dn_tensor *t, const dn_tensor *const *masks, int32_t nmasks, const dn_tensor *a) {
+    dn_status st = check_masks(t, a, masks, nmasks, "MaskedSet");
+    if (st != DN_OK) return st;
+    if (num_elements(a) == 0) return DN_OK;
+    if (t->ndims == 1 && masks[0]) {
+        BoolView m;
+        st = make_bool_view(m, masks[0], "MaskedSet");
+        if (st != DN_OK) return st;
+        const int sz = dtype_size(a->dtype);
+        DN_SWITCH_SIZE(sz, {
+            SetSink<B> sink{data_ptr(t), data_ptr(a), t->stride[0] * sz, a->stride[0] * sz, a->shape[0]};
+            return run_compaction(m, sink);
+        });
+    }
+    return masked_general<false>(a, t, masks, "MaskedSet");
+}
+
+}  // extern "C"
