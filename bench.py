@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 Tensor backend (contract: see the task brief / DESIGN.md §Measurement).
+
+Metric (BASELINE.json): element-wise / reduction HBM GB/s (% of B200 peak) at 1/2/4/8 GPUs vs HostTensor.
+Workload (BASELINE.json configs[1], SURVEY.md §8d "C2"): strided / broadcast element-wise operators on transposed,
+broadcast, sliced and reversed views of [16384, 16384] tensors (2^28 elements) in float32, float64 and int32.
+One "step" = one pass over that whole case list (33 backend calls). `value` = algorithmic bytes of the step,
+summed over all ranks, divided by the step time (max over ranks) — inputs resident in HBM. `e2e` = the same case
+list driven through the public API from PINNED HOST buffers: every step copies the inputs host->device, runs the
+calls, and copies one result per dtype back.
+
+Multi-GPU (`--gpus N`, launched under torchrun): the leading axis is sharded, every rank owns one [16384, 16384]
+slab of every operand (weak scaling); element-wise operators need no collective.
+
+`--impl reference` times the reference's own CPU path for the same case list — the C++ restatement of HostTensor
+in oracle/ (the F# original cannot run in this image: no dotnet), with its threading policy, on the host cores
+of this box, on a bounded sample (2^24-element tensors).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "elementwise/reduction HBM GB/s (% of B200 peak) at 1/2/4/8 GPUs vs HostTensor"
+SIDE = 16384  # 2^28 elements per tensor
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The C2 case list, written once against the frontend so that the CUDA arm, the e2e arm and the CPU arm run the
+# same calls. Each entry: (name, algorithmic bytes, callable).  Algorithmic bytes: every DISTINCT element touched
+# counts once; broadcast operands count their own size.
+# ---------------------------------------------------------------------------------------------------------------
+def build_cases(T, dt, a, b, c, row, col, mask, has_sin: bool):
+    """a, b, c: [R, C]; row: [1, C]; col: [R, 1]; mask: bool [R, C]. Returns the case list for one dtype."""
+    from deepnet_b200 import dtypes
+    s = dtypes.itemsize(dt)
+    R, C = a.Shape
+    N = R * C
+    nm = dtypes.NAMES[dt]
+    cs, as_, bs = c[1:, 1:], a[1:, 1:], b[1:, 1:]
+    ar0, ar1, aT = a.reverseAxis(0), a.reverseAxis(1), a.T
+    cases = [
+        (f"{nm} add contiguous", 3 * N * s, lambda: c.FillAdd(a, b)),
+        (f"{nm} add a.T + b", 3 * N * s, lambda: c.FillAdd(aT, b)),
+        (f"{nm} add a + row[1,C]", (2 * N + C) * s, lambda: c.FillAdd(a, row)),
+        (f"{nm} mul a * col[R,1]", (2 * N + R) * s, lambda: c.FillMultiply(a, col)),
+        (f"{nm} {'sin' if has_sin else 'abs'}(a.T)", 2 * N * s,
+         (lambda: c.FillSin(aT)) if has_sin else (lambda: c.FillAbs(aT))),
+        (f"{nm} add a[1:,1:] + b[1:,1:]", 3 * (R - 1) * (C - 1) * s, lambda: cs.FillAdd(as_, bs)),
+        (f"{nm} add reverseAxis0(a) + b", 3 * N * s, lambda: c.FillAdd(ar0, b)),
+        (f"{nm} add reverseAxis1(a) + b", 3 * N * s, lambda: c.FillAdd(ar1, b)),
+        (f"{nm} copy a.T", 2 * N * s, lambda: c.CopyFrom(aT)),
+        (f"{nm} less a < b.T -> bool", (2 * s + 1) * N, lambda: mask.FillLess(a, b.T)),
+        (f"{nm} ifThenElse(mask, a, b)", (3 * s + 1) * N, lambda: c.FillIfThenElse(mask, a, b)),
+    ]
+    return cases
+
+
+def dtype_list():
+    from deepnet_b200 import dtypes
+    return [(dtypes.DN_F32, np.float32, True), (dtypes.DN_F64, np.float64, True), (dtypes.DN_I32, np.int32, False)]
+
+
+def host_inputs(rng, side, npdt):
+    if np.issubdtype(npdt, np.floating):
+        mk = lambda shape: rng.uniform(-50, 50, size=shape).astype(npdt)
+    else:
+        mk = lambda shape: np.rint(rng.uniform(-50, 50, size=shape)).astype(npdt)
+    return mk((side, side)), mk((side, side)), mk((1, side)), mk((side, 1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md)
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.check_output(
+                    ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                    timeout=5).decode().strip()
+                self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (HostTensor restatement) on a bounded sample
+# ---------------------------------------------------------------------------------------------------------------
+def run_cpu_cases(side: int, steps: int, warmup: int):
+    from deepnet_b200 import Tensor, dtypes
+    from oracle.host_tensor import HostTensor
+    rng = np.random.default_rng(2)
+    per_dtype = []
+    total_bytes = 0
+    for dt, npdt, has_sin in dtype_list():
+        an, bn, rn, cn = host_inputs(rng, side, npdt)
+        a, b, row, col = (HostTensor.ofNumpy(x) for x in (an, bn, rn, cn))
+        c = Tensor.empty((side, side), dt, HostTensor.Dev)
+        mask = Tensor.empty((side, side), dtypes.DN_BOOL, HostTensor.Dev)
+        cases = build_cases(Tensor, dt, a, b, c, row, col, mask, has_sin)
+        per_dtype.append(cases)
+        total_bytes += sum(nb for _, nb, _ in cases)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for cases in per_dtype:
+            for _, _, fn in cases:
+                fn()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    return total_bytes / sec / 1e9, sec, total_bytes
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--side", type=int, default=SIDE, help="tensor side (default 16384 = 2^28 elements)")
+    ap.add_argument("--cpu-side", type=int, default=2048, help="side of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1/C3/C4 side measurements")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    workload = (f"C2: element-wise ops on transposed/broadcast/sliced/reversed views of [{args.side},{args.side}] "
+                f"(2^{int(np.log2(args.side * args.side))} elements) float32+float64+int32, 33 backend calls per step")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        warm = max(1, min(args.warmup, 2))
+        steps = max(1, min(args.steps, 5))
+        gbs, sec, nbytes = run_cpu_cases(args.cpu_side, steps, warm)
+        sample = (f"same 33-call case list on [{args.cpu_side},{args.cpu_side}] tensors "
+                  f"({nbytes / 1e9:.2f} GB algorithmic per step)")
+        line = {
+            "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+f64+i32", "data": "synthetic",
+            "config": {"workload": workload, "reference_arm": "HostTensor restatement (C++/OpenMP, oracle/), not .NET"},
+            "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from deepnet_b200 import CudaTensor, Tensor, dtypes
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = CudaTensor.dev()
+    dev.Init(local_rank)
+    stream = torch.cuda.current_stream()
+    dev.SetStream(stream.cuda_stream)
+    side = args.side
+    torch_dt = {dtypes.DN_F32: torch.float32, dtypes.DN_F64: torch.float64, dtypes.DN_I32: torch.int32}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -------------------------------------------------------------------------------
+    rng = np.random.default_rng(1000 + rank)
+    per_dtype, keep = [], []
+    host_sets = []
+    for dt, npdt, has_sin in dtype_list():
+        g = torch.Generator(device="cuda").manual_seed(17 + rank)
+        if dt == dtypes.DN_I32:
+            mk = lambda shape: torch.randint(-50, 50, shape, device="cuda", dtype=torch.int32, generator=g)
+        else:
+            mk = lambda shape: torch.rand(shape, device="cuda", dtype=torch_dt[dt], generator=g) * 100 - 50
+        ta, tb, trow, tcol = mk((side, side)), mk((side, side)), mk((1, side)), mk((side, 1))
+        tc = torch.empty((side, side), device="cuda", dtype=torch_dt[dt])
+        tm = torch.empty((side, side), device="cuda", dtype=torch.bool)
+        keep += [ta, tb, trow, tcol, tc, tm]
+        w = lambda t, d=dt: CudaTensor.usingPtr(t.data_ptr(), tuple(t.shape), d, owner=t)
+        a, b, row, col, c = w(ta), w(tb), w(trow), w(tcol), w(tc)
+        mask = CudaTensor.usingPtr(tm.data_ptr(), (side, side), dtypes.DN_BOOL, owner=tm)
+        per_dtype.append((dt, build_cases(Tensor, dt, a, b, c, row, col, mask, has_sin), (a, b, c)))
+    step_bytes = sum(nb for _, cases, _ in per_dtype for _, nb, _ in cases)
+    ncalls = sum(len(cases) for _, cases, _ in per_dtype)
+
+    def step():
+        for _, cases, _ in per_dtype:
+            for _, _, fn in cases:
+                fn()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = dev.LaunchCount()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    launches = dev.LaunchCount() - launches0
+    total_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = step_bytes * world / (ms_per_step * 1e-3) / 1e9
+
+    # per-call timing (CUDA events on the launching stream) for the roofline object; outside the timed region
+    per_call = []
+    for _, cases, _ in per_dtype:
+        for name, nb, fn in cases:
+            ts = []
+            for _ in range(5):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(stream)
+                fn()
+                e.record(stream)
+                e.synchronize()
+                ts.append(s.elapsed_time(e))
+            per_call.append((name, nb, statistics.median(ts)))
+    clocks = sampler.stop() if rank == 0 else None
+    peak, peak_src = load_peaks()
+    # dominant kernel = the call with the largest share of the step
+    dom = max(per_call, key=lambda x: x[2])
+    roofline = {
+        "bound": "hbm", "kernel": dom[0], "achieved": dom[1] / dom[2] / 1e6, "peak": peak, "unit": "GB/s",
+        "frac": dom[1] / dom[2] / 1e6 / peak, "traffic": None, "peak_source": peak_src,
+        "share_of_step": dom[2] / sum(x[2] for x in per_call),
+        "per_call_gbs": {n: round(nb / ms / 1e6, 1) for n, nb, ms in per_call},
+        "step_frac_of_peak": (step_bytes / (ms_per_step * 1e-3) / 1e9) / peak if world == 1 else value / world / peak,
+    }
+
+    # ---- e2e arm: pinned host buffers -> H2D -> same calls -> D2H of one result per dtype ---------------------
+    e2e_side = side
+    pinned, e2e_sets = [], []
+    h2d = d2h = 0
+    for dt, npdt, has_sin in dtype_list():
+        an, bn, rn, cn = host_inputs(rng, e2e_side, npdt)
+        hp = [torch.from_numpy(x).pin_memory() for x in (an, bn, rn, cn)]
+        out = torch.empty((e2e_side, e2e_side), dtype=torch_dt[dt]).pin_memory()
+        pinned.append((hp, out))
+        h2d += sum(x.numel() * x.element_size() for x in hp)
+        d2h += out.numel() * out.element_size()
+    api = dev.api
+
+    def e2e_step():
+        for (dt, cases, (a, b, c)), (hp, out), (_, _, _) in zip(per_dtype, pinned, dtype_list()):
+            isz = dtypes.itemsize(dt)
+            # Transfer host->device through the C ABI (dn_memcpy_h2d, async on the stream from pinned memory)
+            api.call("memcpy_h2d", a.Storage.BasePtr(), hp[0].data_ptr(), hp[0].numel() * isz)
+            api.call("memcpy_h2d", b.Storage.BasePtr(), hp[1].data_ptr(), hp[1].numel() * isz)
+            for _, _, fn in cases:
+                fn()
+            api.call("memcpy_d2h", out.data_ptr(), c.Storage.BasePtr(), out.numel() * isz)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record(stream)
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1) / e2e_steps
+    t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = step_bytes * world / (e2e_ms * 1e-3) / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32+f64+i32", "data": "synthetic",
+        "config": {"workload": workload, "calls_per_step": ncalls, "algorithmic_bytes_per_step_per_gpu": step_bytes,
+                   "l2": "inputs (1-2 GiB each) are far larger than the 126 MB L2; no flush needed",
+                   "parallelism": f"leading-axis shards x{world}, no collective"},
+        "frac_of_peak": value / world / peak, "peak_gbs": peak, "peak_source": peak_src,
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        gbs, sec, nbytes = run_cpu_cases(args.cpu_side, 2, 1)
+        line["cpu_baseline"] = {
+            "value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": f"same 33-call case list on [{args.cpu_side},{args.cpu_side}] tensors "
+                      f"({nbytes / 1e9:.2f} GB algorithmic per step, {sec:.2f} s per step); HostTensor restatement "
+                      f"(C++/OpenMP) with the reference's threading policy, not .NET"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -5,13 +5,16 @@
 // Design (B200, HBM-bound):
 //   * The host canonicalises the operand layouts (ew_plan.cu): drops size-1 dims, flips negative target strides,
 //     sorts dims by target stride, merges dims that are contiguous in EVERY operand. What is left is usually 1-D.
-//   * ew_kernel<F, VEC>: one template for all ranks. Work items are VEC consecutive elements of the innermost
-//     dim; every thread keeps U independent items in flight (U*VEC*size >= 64 bytes of loads per operand).
-//     VEC > 1 needs every operand's innermost stride to be 1 (vector access) or 0 (splat) and 16-byte alignment;
-//     anything else runs VEC = 1, still coalesced along the target's fastest dim. Index math is 32-bit with
-//     multiply-shift division, per work item, not per element.
-//   * ew_tiled_kernel<F>: when a source's unit-stride dim differs from the target's (transposed views), a
-//     32x32 tile of that source is staged through shared memory so both sides are accessed with full sectors.
+//   * ew_kernel<F, VEC, U, ND>: work items are VEC consecutive elements of the innermost dim (32 bytes on the
+//     widest operand); every thread keeps U independent items in flight. VEC > 1 needs every operand's innermost
+//     stride to be 1 (vector access) or 0 (splat) and 16-byte alignment; anything else runs VEC = 1, still
+//     coalesced along the target's fastest dim, with the rank fixed at compile time (ND = 1, 2, 3) so that the
+//     per-element index math is a couple of multiply-shift divisions. Index math is 32-bit.
+//   * ew_xpose_kernel<F, M>: when a source's unit-stride dim (dS) differs from the target's (dT) — transposed
+//     views — every thread owns an M x M micro-tile: it reads the "S-type" sources as M vectors along dS, the
+//     "T-type" sources as M vectors along dT, transposes in REGISTERS and writes M vectors along dT. Lanes are
+//     laid out 8 (dS) x 4 (dT), so every warp-level access covers whole 32-byte sectors on both sides; no shared
+//     memory, no barriers.
 //   * Aliasing: target and sources may be the same memory (f3.FillMultiply f3 e, Tensor.Sample/Program.fs:186),
 //     so no __restrict__ / ld.global.nc; every thread reads all its inputs before it writes.
 #pragma once
@@ -39,7 +42,7 @@ struct EwPlan {
     int64_t n = 0;  // total elements; 0 = nothing to do
 };
 
-// Builds the canonical plan. `srcs[k] == nullptr` with `index_dim >= 0` inserts the virtual index operand.
+// Builds the canonical plan. `index_operand >= 0` makes that source the virtual index operand along `index_dim`.
 dn_status ew_make_plan(EwPlan &plan, const dn_tensor *t, const dn_tensor *const *srcs, int nsrc,
                        int index_operand = -1, int index_dim = -1);
 
@@ -58,7 +61,7 @@ struct IndexT {};  // tag type of the virtual index operand; its loaded value is
 
 template <class T> struct LoadedType { using type = T; };
 template <> struct LoadedType<IndexT> { using type = int64_t; };
-template <class T> constexpr int ew_sizeof() { return std::is_same<T, IndexT>::value ? 1 : (int)sizeof(T); }
+template <> struct LoadedType<void> { using type = char; };
 
 // ---- packs -------------------------------------------------------------------------------------------------
 template <class T, int N>
@@ -126,6 +129,10 @@ struct InPack {
         }
     }
 };
+template <int VEC>
+struct InPack<void, VEC> {
+    __device__ __forceinline__ void load(const char *, bool) {}
+};
 
 // Functor signature helper: every functor derives from EwSig<Out, In0[, In1[, In2]]>.
 template <class T> constexpr int ew_vec_size() {
@@ -133,7 +140,13 @@ template <class T> constexpr int ew_vec_size() {
     else return (int)sizeof(T);
 }
 constexpr int ew_cmax(int a, int b) { return a > b ? a : b; }
+constexpr int ew_cmin(int a, int b) { return a < b ? a : b; }
 constexpr int ew_cmin_nz(int a, int b) { return a == 0 ? b : (b == 0 ? a : (a < b ? a : b)); }
+constexpr int ew_pick_vec(int min_size, int max_size) {
+    int v = ew_cmax(16 / min_size, 32 / max_size);
+    while (v > 1 && v * max_size > 64) v /= 2;
+    return v;
+}
 
 template <class OutT, class A = void, class B = void, class C = void>
 struct EwSig {
@@ -147,45 +160,48 @@ struct EwSig {
         ew_cmax(ew_cmax((int)sizeof(OutT), ew_vec_size<A>()), ew_cmax(ew_vec_size<B>(), ew_vec_size<C>()));
     static constexpr int MinSize =
         ew_cmin_nz(ew_cmin_nz((int)sizeof(OutT), ew_vec_size<A>()), ew_cmin_nz(ew_vec_size<B>(), ew_vec_size<C>()));
-    // elements per vector work item: 16-byte accesses on the narrowest operand, at most 64 bytes on the widest
-    static constexpr int Vec = (16 / MinSize) < (64 / MaxSize) ? (16 / MinSize) : (64 / MaxSize);
-    static constexpr bool Tiled = true;  // instantiate the shared-memory transpose kernel for this functor
+    // elements per vector work item: at least 16 bytes on the narrowest operand, 32 bytes on the widest if that
+    // does not push the widest past 64 bytes
+    static constexpr int Vec = ew_pick_vec(MinSize, MaxSize);
+    static constexpr bool Tiled = true;  // instantiate the register-transpose kernel for this functor
 };
 
-template <int VEC>
-struct InPack<void, VEC> {
-    __device__ __forceinline__ void load(const char *, bool) {}
-};
-
-template <class F, int K> struct InType;
-template <class F> struct InType<F, 0> { using type = typename F::In0; };
-template <class F> struct InType<F, 1> { using type = typename F::In1; };
-template <class F> struct InType<F, 2> { using type = typename F::In2; };
-template <class T> struct SmemType { using type = typename LoadedType<T>::type; };
-template <> struct SmemType<void> { using type = char; };
-
-template <int NOPS>
+template <int NOPS, int ND>
 __device__ __forceinline__ void ew_offsets(const EwParams<NOPS> &p, uint32_t idx, int64_t (&off)[NOPS]) {
 #pragma unroll
     for (int k = 0; k < NOPS; ++k) off[k] = 0;
     uint32_t rem = idx;
+    if constexpr (ND > 0) {
 #pragma unroll
-    for (int d = 0; d < DN_MAX_DIMS; ++d) {
-        if (d == p.ndims - 1) {
+        for (int d = 0; d < ND; ++d) {
+            uint32_t x = rem;
+            if (d < ND - 1) {
+                const uint32_t q = p.div[d].div(rem);
+                x = rem - q * p.shape[d];
+                rem = q;
+            }
 #pragma unroll
-            for (int k = 0; k < NOPS; ++k) off[k] += (int64_t)rem * p.stride[k][d];
-            break;
+            for (int k = 0; k < NOPS; ++k) off[k] += (int64_t)x * p.stride[k][d];
         }
-        const uint32_t q = p.div[d].div(rem);
-        const uint32_t r = rem - q * p.shape[d];
+    } else {
 #pragma unroll
-        for (int k = 0; k < NOPS; ++k) off[k] += (int64_t)r * p.stride[k][d];
-        rem = q;
+        for (int d = 0; d < DN_MAX_DIMS; ++d) {
+            if (d == p.ndims - 1) {
+#pragma unroll
+                for (int k = 0; k < NOPS; ++k) off[k] += (int64_t)rem * p.stride[k][d];
+                break;
+            }
+            const uint32_t q = p.div[d].div(rem);
+            const uint32_t r = rem - q * p.shape[d];
+#pragma unroll
+            for (int k = 0; k < NOPS; ++k) off[k] += (int64_t)r * p.stride[k][d];
+            rem = q;
+        }
     }
 }
 
-// F: struct { using Out; using In0[, In1, In2]; static constexpr int NSRC; __device__ Out operator()(...) const; }
-template <class F, int VEC, int U>
+// F: struct : EwSig<...> { __device__ Out operator()(In...) const; }
+template <class F, int VEC, int U, int ND>
 __global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ EwParams<F::NSRC + 1> p, const F f) {
     constexpr int NOPS = F::NSRC + 1;
     using Out = typename F::Out;
@@ -204,7 +220,7 @@ __global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ 
             const uint64_t idx = base + (uint32_t)j * kEwThreads + threadIdx.x;
             if (idx < p.n) {
                 int64_t off[NOPS];
-                ew_offsets<NOPS>(p, (uint32_t)idx, off);
+                ew_offsets<NOPS, ND>(p, (uint32_t)idx, off);
                 toff[j] = off[0];
                 if constexpr (F::NSRC > 0) a[j].load(p.ptr[1] + off[1], (p.splat_mask >> 1) & 1);
                 if constexpr (F::NSRC > 1) b[j].load(p.ptr[2] + off[2], (p.splat_mask >> 2) & 1);
@@ -229,19 +245,19 @@ __global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ 
     }
 }
 
-// ---- tiled kernel for transposed sources ---------------------------------------------------------------------
-// Dims: dT = canonical dim 0 (target stride 1), dS = the dim in which the "S-type" sources have stride 1.
-// A CTA (32 x 8 threads) handles one 32(dT) x 32(dS) tile; S-type sources are read with threadIdx.x along dS
-// into padded shared memory and consumed with threadIdx.x along dT; T-type sources and the target are accessed
-// directly with threadIdx.x along dT. Batch dims (all others) are decomposed once per CTA.
-constexpr int kTile = 32;
-constexpr int kTileRows = 8;
-
+// ---- register-transpose kernel for transposed sources ----------------------------------------------------------
+// Dims: dT = canonical dim 0 (target stride 1), dS = the dim in which the "S-type" sources have stride 1; every
+// other dim is a batch dim decomposed once per CTA. Operand access modes (2 bits each in `modes`):
+//   0 = T-vector: unit stride along dT, aligned   -> M vector accesses along dT (one per dS position)
+//   1 = S-vector: unit stride along dS, aligned   -> M vector accesses along dS (one per dT position)
+//   2 = scalar:   anything else (broadcast, misaligned, arbitrary strides) -> M*M element accesses
+// CTA = 8 warps as 2 (dS) x 4 (dT); warp = 8 lanes (dS) x 4 lanes (dT); thread = K micro-tiles of M x M elements
+// stepped along dS. CTA tile: 16*M*K (dS) x 16*M (dT).
 template <int NOPS>
-struct EwTiledParams {
+struct EwXposeParams {
     char *ptr[NOPS];
-    int64_t strideT[NOPS];  // bytes per step along dT
-    int64_t strideS[NOPS];  // bytes per step along dS
+    int64_t strideT[NOPS];  // bytes per element step along dT
+    int64_t strideS[NOPS];  // bytes per element step along dS
     int64_t strideB[NOPS][DN_MAX_DIMS];  // bytes per step of batch dim b
     uint32_t shapeB[DN_MAX_DIMS];
     FastDiv divB[DN_MAX_DIMS];
@@ -249,28 +265,60 @@ struct EwTiledParams {
     uint32_t sizeT, sizeS;
     uint32_t tilesT, tilesS;
     FastDiv divTilesT, divTilesS;
-    uint32_t smem_mask;  // bit k: operand k is S-type (staged through shared memory)
+    uint32_t modes;  // 2 bits per operand
 };
 
 template <class T>
 __device__ __forceinline__ typename LoadedType<T>::type ew_load_elem(const char *addr) {
     if constexpr (std::is_same<T, IndexT>::value) return (int64_t)(intptr_t)addr;
+    else if constexpr (std::is_void<T>::value) return 0;
     else return *reinterpret_cast<const T *>(addr);
 }
 
-template <class F>
-__global__ void __launch_bounds__(kTile *kTileRows) ew_tiled_kernel(const __grid_constant__ EwTiledParams<F::NSRC + 1> p,
-                                                                  const F f) {
+// val[j][i] = element at (dS position s0+j, dT position t0+i)
+template <class T, int M>
+__device__ __forceinline__ void xpose_load(typename LoadedType<T>::type (&val)[M][M], const char *base, int64_t strideT,
+                                           int64_t strideS, int mode) {
+    if constexpr (std::is_void<T>::value) {
+        return;
+    } else if constexpr (std::is_same<T, IndexT>::value) {
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+            for (int i = 0; i < M; ++i) val[j][i] = (int64_t)(intptr_t)(base + i * strideT + j * strideS);
+    } else {
+        if (mode == 0) {
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const Pack<T, M> v = load_pack<Pack<T, M>>(base + j * strideS);
+#pragma unroll
+                for (int i = 0; i < M; ++i) val[j][i] = v.v[i];
+            }
+        } else if (mode == 1) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const Pack<T, M> v = load_pack<Pack<T, M>>(base + i * strideT);
+#pragma unroll
+                for (int j = 0; j < M; ++j) val[j][i] = v.v[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < M; ++j)
+#pragma unroll
+                for (int i = 0; i < M; ++i) val[j][i] = *reinterpret_cast<const T *>(base + i * strideT + j * strideS);
+        }
+    }
+}
+
+template <class F, int M, int K>
+__global__ void __launch_bounds__(kEwThreads) ew_xpose_kernel(const __grid_constant__ EwXposeParams<F::NSRC + 1> p,
+                                                            const F f) {
     constexpr int NOPS = F::NSRC + 1;
     using Out = typename F::Out;
-    using L0 = typename SmemType<typename F::In0>::type;
-    using L1 = typename SmemType<typename F::In1>::type;
-    using L2 = typename SmemType<typename F::In2>::type;
-    __shared__ L0 s0[kTile][kTile + 1];
-    __shared__ L1 s1[F::NSRC > 1 ? kTile : 1][kTile + 1];
-    __shared__ L2 s2[F::NSRC > 2 ? kTile : 1][kTile + 1];
+    using L0 = typename LoadedType<typename F::In0>::type;
+    using L1 = typename LoadedType<typename F::In1>::type;
+    using L2 = typename LoadedType<typename F::In2>::type;
 
-    // blockIdx.x -> (tileT, tileS, batch...)
     uint32_t rem = blockIdx.x;
     uint32_t q = p.divTilesT.div(rem);
     const uint32_t tT = rem - q * p.tilesT;
@@ -290,73 +338,132 @@ __global__ void __launch_bounds__(kTile *kTileRows) ew_tiled_kernel(const __grid
         for (int k = 0; k < NOPS; ++k) boff[k] += (int64_t)r * p.strideB[k][d];
         rem = qq;
     }
-    const uint32_t t0 = tT * kTile, sbase = tS * kTile;
-    const uint32_t tx = threadIdx.x, ty = threadIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t t0 = (tT * 16 + (warp >> 1) * 4 + (lane >> 3)) * M;
+    const uint32_t sbase = (tS * 16 * K + (warp & 1) * 8 * K + (lane & 7)) * M;  // + kk*8*M per micro-tile
+    if (t0 >= p.sizeT) return;
 
-    // stage S-type sources: threadIdx.x runs along dS (their unit-stride dim)
+    const bool t_full = t0 + M <= p.sizeT;
+    // Fast path: every operand is accessed with vectors (modes 0/1) and all K micro-tiles are interior. All loads
+    // of all operands are issued back to back (no per-operand branches), then transposed with selects.
+    if ((p.modes & 0xAAu) == 0 && (p.modes & 3u) == 0 && t_full && sbase + (K - 1) * 8 * M + M <= p.sizeS) {
+        using V0 = Pack<std::conditional_t<std::is_void<typename F::In0>::value, char, typename F::In0>, M>;
+        using V1 = Pack<std::conditional_t<std::is_void<typename F::In1>::value, char, typename F::In1>, M>;
+        using V2 = Pack<std::conditional_t<std::is_void<typename F::In2>::value, char, typename F::In2>, M>;
+        V0 va[K][M];
+        V1 vb[K][M];
+        V2 vc[K][M];
+        const bool m1 = (p.modes >> 2) & 1, m2 = (p.modes >> 4) & 1, m3 = (p.modes >> 6) & 1;
+        const int64_t st1 = m1 ? p.strideT[1] : p.strideS[1];  // step between the M vectors of operand 1
+        const int64_t st2 = m2 ? p.strideT[2] : p.strideS[2];
+        const int64_t st3 = m3 ? p.strideT[3] : p.strideS[3];
 #pragma unroll
-    for (int i = 0; i < kTile; i += kTileRows) {
-        const uint32_t tpos = t0 + ty + i, spos = sbase + tx;
-        if (tpos < p.sizeT && spos < p.sizeS) {
+        for (int kk = 0; kk < K; ++kk) {
+            const uint32_t s0 = sbase + kk * 8 * M;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                if constexpr (F::NSRC > 0 && !std::is_same<typename F::In0, IndexT>::value)
+                    va[kk][m] = load_pack<V0>(p.ptr[1] + boff[1] + (int64_t)t0 * p.strideT[1] + (int64_t)s0 * p.strideS[1] + m * st1);
+                if constexpr (F::NSRC > 1 && !std::is_same<typename F::In1, IndexT>::value)
+                    vb[kk][m] = load_pack<V1>(p.ptr[2] + boff[2] + (int64_t)t0 * p.strideT[2] + (int64_t)s0 * p.strideS[2] + m * st2);
+                if constexpr (F::NSRC > 2 && !std::is_same<typename F::In2, IndexT>::value)
+                    vc[kk][m] = load_pack<V2>(p.ptr[3] + boff[3] + (int64_t)t0 * p.strideT[3] + (int64_t)s0 * p.strideS[3] + m * st3);
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) {
+            const uint32_t s0 = sbase + kk * 8 * M;
+            char *tbase = p.ptr[0] + boff[0] + (int64_t)t0 * p.strideT[0] + (int64_t)s0 * p.strideS[0];
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                Pack<Out, M> r;
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    // element (dS = s0+j, dT = t0+i): mode 0 -> vector j, lane i; mode 1 -> vector i, lane j
+                    if constexpr (F::NSRC == 1) r.v[i] = f(m1 ? va[kk][i].v[j] : va[kk][j].v[i]);
+                    else if constexpr (F::NSRC == 2)
+                        r.v[i] = f(m1 ? va[kk][i].v[j] : va[kk][j].v[i], m2 ? vb[kk][i].v[j] : vb[kk][j].v[i]);
+                    else
+                        r.v[i] = f(m1 ? va[kk][i].v[j] : va[kk][j].v[i], m2 ? vb[kk][i].v[j] : vb[kk][j].v[i],
+                                   m3 ? vc[kk][i].v[j] : vc[kk][j].v[i]);
+                }
+                store_pack(tbase + j * p.strideS[0], r);
+            }
+        }
+        return;
+    }
+
+    L0 a[K][M][M];
+    L1 b[K][M][M];
+    L2 c[K][M][M];
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) {
+        const uint32_t s0 = sbase + kk * 8 * M;
+        if (t_full && s0 + M <= p.sizeS) {
             if constexpr (F::NSRC > 0)
-                if ((p.smem_mask >> 1) & 1)
-                    s0[ty + i][tx] = ew_load_elem<typename F::In0>(
-                        p.ptr[1] + boff[1] + (int64_t)tpos * p.strideT[1] + (int64_t)spos * p.strideS[1]);
+                xpose_load<typename F::In0, M>(a[kk], p.ptr[1] + boff[1] + (int64_t)t0 * p.strideT[1] + (int64_t)s0 * p.strideS[1],
+                                               p.strideT[1], p.strideS[1], (p.modes >> 2) & 3);
             if constexpr (F::NSRC > 1)
-                if ((p.smem_mask >> 2) & 1)
-                    s1[ty + i][tx] = ew_load_elem<typename F::In1>(
-                        p.ptr[2] + boff[2] + (int64_t)tpos * p.strideT[2] + (int64_t)spos * p.strideS[2]);
+                xpose_load<typename F::In1, M>(b[kk], p.ptr[2] + boff[2] + (int64_t)t0 * p.strideT[2] + (int64_t)s0 * p.strideS[2],
+                                               p.strideT[2], p.strideS[2], (p.modes >> 4) & 3);
             if constexpr (F::NSRC > 2)
-                if ((p.smem_mask >> 3) & 1)
-                    s2[ty + i][tx] = ew_load_elem<typename F::In2>(
-                        p.ptr[3] + boff[3] + (int64_t)tpos * p.strideT[3] + (int64_t)spos * p.strideS[3]);
+                xpose_load<typename F::In2, M>(c[kk], p.ptr[3] + boff[3] + (int64_t)t0 * p.strideT[3] + (int64_t)s0 * p.strideS[3],
+                                               p.strideT[3], p.strideS[3], (p.modes >> 6) & 3);
         }
     }
-    __syncthreads();
-    // compute: threadIdx.x runs along dT
 #pragma unroll
-    for (int i = 0; i < kTile; i += kTileRows) {
-        const uint32_t tpos = t0 + tx, spos = sbase + ty + i;
-        if (tpos < p.sizeT && spos < p.sizeS) {
-            Out r;
-            if constexpr (F::NSRC == 1) {
-                L0 a = ((p.smem_mask >> 1) & 1) ? s0[tx][ty + i]
-                                                : ew_load_elem<typename F::In0>(
-                                                      p.ptr[1] + boff[1] + (int64_t)tpos * p.strideT[1] + (int64_t)spos * p.strideS[1]);
-                r = f(a);
-            } else if constexpr (F::NSRC == 2) {
-                L0 a = ((p.smem_mask >> 1) & 1) ? s0[tx][ty + i]
-                                                : ew_load_elem<typename F::In0>(
-                                                      p.ptr[1] + boff[1] + (int64_t)tpos * p.strideT[1] + (int64_t)spos * p.strideS[1]);
-                L1 b = ((p.smem_mask >> 2) & 1) ? s1[tx][ty + i]
-                                                : ew_load_elem<typename F::In1>(
-                                                      p.ptr[2] + boff[2] + (int64_t)tpos * p.strideT[2] + (int64_t)spos * p.strideS[2]);
-                r = f(a, b);
-            } else if constexpr (F::NSRC == 3) {
-                L0 a = ((p.smem_mask >> 1) & 1) ? s0[tx][ty + i]
-                                                : ew_load_elem<typename F::In0>(
-                                                      p.ptr[1] + boff[1] + (int64_t)tpos * p.strideT[1] + (int64_t)spos * p.strideS[1]);
-                L1 b = ((p.smem_mask >> 2) & 1) ? s1[tx][ty + i]
-                                                : ew_load_elem<typename F::In1>(
-                                                      p.ptr[2] + boff[2] + (int64_t)tpos * p.strideT[2] + (int64_t)spos * p.strideS[2]);
-                L2 c = ((p.smem_mask >> 3) & 1) ? s2[tx][ty + i]
-                                                : ew_load_elem<typename F::In2>(
-                                                      p.ptr[3] + boff[3] + (int64_t)tpos * p.strideT[3] + (int64_t)spos * p.strideS[3]);
-                r = f(a, b, c);
+    for (int kk = 0; kk < K; ++kk) {
+        const uint32_t s0 = sbase + kk * 8 * M;
+        if (s0 >= p.sizeS) continue;
+        char *tbase = p.ptr[0] + boff[0] + (int64_t)t0 * p.strideT[0] + (int64_t)s0 * p.strideS[0];
+        if (t_full && s0 + M <= p.sizeS) {
+            const int tmode = p.modes & 3;
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                Pack<Out, M> r;
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    if constexpr (F::NSRC == 1) r.v[i] = f(a[kk][j][i]);
+                    else if constexpr (F::NSRC == 2) r.v[i] = f(a[kk][j][i], b[kk][j][i]);
+                    else r.v[i] = f(a[kk][j][i], b[kk][j][i], c[kk][j][i]);
+                }
+                if (tmode == 0) {
+                    store_pack(tbase + j * p.strideS[0], r);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < M; ++i)
+                        *reinterpret_cast<Out *>(tbase + i * p.strideT[0] + j * p.strideS[0]) = r.v[i];
+                }
             }
-            *reinterpret_cast<Out *>(p.ptr[0] + boff[0] + (int64_t)tpos * p.strideT[0] + (int64_t)spos * p.strideS[0]) = r;
+        } else {
+            // edge micro-tile: element-wise, predicated
+            for (int j = 0; j < M; ++j)
+                for (int i = 0; i < M; ++i) {
+                    if (t0 + i >= p.sizeT || s0 + j >= p.sizeS) continue;
+                    Out r;
+                    if constexpr (F::NSRC == 1) {
+                        r = f(ew_load_elem<typename F::In0>(p.ptr[1] + boff[1] + (int64_t)(t0 + i) * p.strideT[1] + (int64_t)(s0 + j) * p.strideS[1]));
+                    } else if constexpr (F::NSRC == 2) {
+                        r = f(ew_load_elem<typename F::In0>(p.ptr[1] + boff[1] + (int64_t)(t0 + i) * p.strideT[1] + (int64_t)(s0 + j) * p.strideS[1]),
+                              ew_load_elem<typename F::In1>(p.ptr[2] + boff[2] + (int64_t)(t0 + i) * p.strideT[2] + (int64_t)(s0 + j) * p.strideS[2]));
+                    } else {
+                        r = f(ew_load_elem<typename F::In0>(p.ptr[1] + boff[1] + (int64_t)(t0 + i) * p.strideT[1] + (int64_t)(s0 + j) * p.strideS[1]),
+                              ew_load_elem<typename F::In1>(p.ptr[2] + boff[2] + (int64_t)(t0 + i) * p.strideT[2] + (int64_t)(s0 + j) * p.strideS[2]),
+                              ew_load_elem<typename F::In2>(p.ptr[3] + boff[3] + (int64_t)(t0 + i) * p.strideT[3] + (int64_t)(s0 + j) * p.strideS[3]));
+                    }
+                    *reinterpret_cast<Out *>(tbase + i * p.strideT[0] + j * p.strideS[0]) = r;
+                }
         }
     }
 }
 
 // ---- host-side launch logic (non-template parts live in ew_plan.cu) ------------------------------------------
-// Decides whether the plan can run with VEC-wide accesses; align[k] = required byte alignment of operand k.
 bool ew_can_vectorize(const EwPlan &plan, int vec, const int *esize, int64_t *tail_elems);
-// Picks dS for the tiled kernel, or returns -1 when the tiled kernel does not apply.
+// Picks dS for the transpose kernel, or returns -1 when it does not apply.
 int ew_pick_tiled_dim(const EwPlan &plan);
-// Chunking of the outermost dim so that one launch covers < 2^31 work items.
-int64_t ew_chunk_rows(const EwPlan &plan, int64_t inner_items);
 int ew_grid_for(int64_t work_items, int items_per_cta);
+// Access mode (0 T-vector, 1 S-vector, 2 scalar) of operand k for micro-tile size m.
+int ew_xpose_mode(const EwPlan &plan, int k, int dS, int m);
 
 template <int NOPS>
 void ew_fill_params(EwParams<NOPS> &p, const EwPlan &plan, int vec, int64_t outer_begin, int64_t outer_count) {
@@ -367,8 +474,7 @@ void ew_fill_params(EwParams<NOPS> &p, const EwPlan &plan, int vec, int64_t oute
     for (int d = 0; d < DN_MAX_DIMS; ++d) {
         int64_t s = d < nd ? plan.shape[d] : 1;
         if (d == 0) s /= vec;
-        if (d == nd - 1 && nd > 1) s = outer_count;
-        if (nd == 1 && d == 0) s = outer_count;  // 1-D: the chunk is over work items directly
+        if (d == nd - 1) s = outer_count;  // the chunk runs along the outermost dim (work items when nd == 1)
         p.shape[d] = (uint32_t)s;
         p.div[d].init((uint32_t)(s > 0 ? s : 1));
         if (d < nd) n *= (uint64_t)s;
@@ -382,29 +488,29 @@ void ew_fill_params(EwParams<NOPS> &p, const EwPlan &plan, int vec, int64_t oute
             p.stride[k][d] = st;
         }
         if (o.stride[0] == 0) p.splat_mask |= 1u << k;
-        // advance to the chunk start along the outermost dim (in work items for 1-D)
         const int od = nd - 1;
-        int64_t step = o.stride[od] * o.esize * ((nd == 1) ? vec : 1);
+        const int64_t step = o.stride[od] * o.esize * ((nd == 1) ? vec : 1);
         p.ptr[k] = o.ptr + outer_begin * step;
     }
 }
 
-template <class F>
-dn_status ew_launch_tiled(const EwPlan &plan, const F &f, int dS);
+template <class F, int VEC, int U, int ND>
+void ew_launch_one(const EwParams<F::NSRC + 1> &p, const F &f) {
+    const int grid = ew_grid_for(p.n, kEwThreads * U);
+    DN_LAUNCH((ew_kernel<F, VEC, U, ND>), grid, kEwThreads, 0, p, f);
+}
 
 template <class F, int VEC>
 dn_status ew_launch_strided(const EwPlan &plan, const F &f, int64_t n_inner0_elems) {
     constexpr int NOPS = F::NSRC + 1;
-    // U: keep >= 64 bytes of loads per source in flight per thread, within a sane register budget
-    constexpr int maxsz = F::MaxSize;
-    constexpr int U = (VEC * maxsz >= 64) ? 1 : ((VEC * maxsz >= 32) ? 2 : 4);
+    // U: independent work items per thread; 64-128 bytes of loads per source in flight per thread
+    constexpr int U = VEC == 1 ? (F::MaxSize >= 8 ? 4 : 8) : ((VEC * F::MaxSize >= 64) ? 1 : ((VEC * F::MaxSize >= 32) ? 2 : 4));
     const int nd = plan.ndims;
-    // inner items = product of all dims but the outermost, in work items
-    int64_t inner = 1;
+    int64_t inner = 1;  // work items of all dims but the outermost
     for (int d = 0; d < nd - 1; ++d) inner *= (d == 0 ? n_inner0_elems / VEC : plan.shape[d]);
     const int64_t outer_total = (nd == 1) ? n_inner0_elems / VEC : plan.shape[nd - 1];
     const int64_t max_items = (int64_t)1 << 30;
-    int64_t chunk = inner > 0 ? max_items / inner : max_items;
+    const int64_t chunk = inner > 0 ? max_items / inner : max_items;
     if (chunk < 1) return set_error(DN_ERR_UNSUPPORTED, "element-wise: inner extent exceeds 2^30 work items");
     EwPlan local = plan;
     local.shape[0] = n_inner0_elems;
@@ -413,13 +519,23 @@ dn_status ew_launch_strided(const EwPlan &plan, const F &f, int64_t n_inner0_ele
         EwParams<NOPS> p;
         ew_fill_params<NOPS>(p, local, VEC, begin, count);
         if (p.n == 0) continue;
-        const int grid = ew_grid_for(p.n, kEwThreads * U);
-        DN_LAUNCH((ew_kernel<F, VEC, U>), grid, kEwThreads, 0, p, f);
+        if constexpr (VEC == 1) {
+            // scalar path: the rank is a compile-time constant for the common cases
+            if (nd == 1) ew_launch_one<F, 1, U, 1>(p, f);
+            else if (nd == 2) ew_launch_one<F, 1, U, 2>(p, f);
+            else if (nd == 3) ew_launch_one<F, 1, U, 3>(p, f);
+            else ew_launch_one<F, 1, U, 0>(p, f);
+        } else {
+            ew_launch_one<F, VEC, U, 0>(p, f);
+        }
     }
     return launch_status("element-wise kernel");
 }
 
-// Entry: run functor F over the plan. VECW = elements per vector work item (16 / smallest element size, capped).
+template <class F>
+dn_status ew_launch_xpose(const EwPlan &plan, const F &f, int dS);
+
+// Entry: run functor F over the plan.
 template <class F>
 dn_status ew_run(EwPlan &plan, const F &f) {
     if (plan.n == 0) return DN_OK;
@@ -446,28 +562,31 @@ dn_status ew_run(EwPlan &plan, const F &f) {
     }
     if constexpr (F::NSRC > 0 && F::Tiled) {
         const int dS = ew_pick_tiled_dim(plan);
-        if (dS > 0) return ew_launch_tiled<F>(plan, f, dS);
+        if (dS > 0) return ew_launch_xpose<F>(plan, f, dS);
     }
     return ew_launch_strided<F, 1>(plan, f, plan.shape[0]);
 }
 
 template <class F>
-dn_status ew_launch_tiled(const EwPlan &plan, const F &f, int dS) {
+dn_status ew_launch_xpose(const EwPlan &plan, const F &f, int dS) {
     constexpr int NOPS = F::NSRC + 1;
-    EwTiledParams<NOPS> p;
+    // micro-tile: 4x4 elements, 2x2 when an 8-byte type is involved (vectors stay <= 16 bytes)
+    constexpr int M = F::MaxSize >= 8 ? 2 : 4;
+    constexpr int K = F::MaxSize >= 8 ? 4 : 1;
+    EwXposeParams<NOPS> p;
     const int nd = plan.ndims;
     p.sizeT = (uint32_t)plan.shape[0];
     p.sizeS = (uint32_t)plan.shape[dS];
-    p.tilesT = (p.sizeT + kTile - 1) / kTile;
-    p.tilesS = (p.sizeS + kTile - 1) / kTile;
+    p.tilesT = (p.sizeT + 16 * M - 1) / (16 * M);
+    p.tilesS = (p.sizeS + 16 * M * K - 1) / (16 * M * K);
     p.divTilesT.init(p.tilesT);
     p.divTilesS.init(p.tilesS);
-    p.smem_mask = 0;
     int nb = 0;
     int64_t nbatch = 1;
     for (int d = 0; d < DN_MAX_DIMS; ++d) {
         p.shapeB[d] = 1;
         p.divB[d].init(1);
+        for (int k = 0; k < NOPS; ++k) p.strideB[k][d] = 0;
     }
     for (int d = 1; d < nd; ++d) {
         if (d == dS) continue;
@@ -477,21 +596,18 @@ dn_status ew_launch_tiled(const EwPlan &plan, const F &f, int dS) {
         nbatch *= plan.shape[d];
         ++nb;
     }
-    for (int k = 0; k < NOPS; ++k)
-        for (int d = nb; d < DN_MAX_DIMS; ++d) p.strideB[k][d] = 0;
     p.nbatch_dims = nb;
+    p.modes = 0;
     for (int k = 0; k < NOPS; ++k) {
         p.ptr[k] = plan.op[k].ptr;
         p.strideT[k] = plan.op[k].stride[0] * plan.op[k].esize;
         p.strideS[k] = plan.op[k].stride[dS] * plan.op[k].esize;
-        if (k > 0 && !plan.op[k].is_index && plan.op[k].stride[dS] == 1 && plan.op[k].stride[0] != 1 &&
-            plan.op[k].stride[0] != 0)
-            p.smem_mask |= 1u << k;
+        p.modes |= (uint32_t)ew_xpose_mode(plan, k, dS, M) << (2 * k);
     }
     const int64_t tiles = (int64_t)p.tilesT * p.tilesS * nbatch;
     if (tiles >= ((int64_t)1 << 31)) return ew_launch_strided<F, 1>(plan, f, plan.shape[0]);
-    DN_LAUNCH((ew_tiled_kernel<F>), (unsigned)tiles, dim3(kTile, kTileRows), 0, p, f);
-    return launch_status("element-wise tiled kernel");
+    DN_LAUNCH((ew_xpose_kernel<F, M, K>), (unsigned)tiles, kEwThreads, 0, p, f);
+    return launch_status("element-wise transpose kernel");
 }
 
 }  // namespace dn

@@ -169,6 +169,7 @@ struct SelectF : EwSig<B, bool8, B, B> {
 // FillIncrementing (ScalarOps.fs:367-370): start + incr * conv(pos0), two roundings for floats (never fused).
 template <class T>
 struct FillIncrF : EwSig<T, IndexT> {
+    static constexpr bool Tiled = false;
     T start, incr;
     __device__ __forceinline__ T operator()(int64_t pos) const {
         if constexpr (std::is_same<T, float>::value) return __fadd_rn(start, __fmul_rn(incr, (float)pos));

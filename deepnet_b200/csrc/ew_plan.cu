@@ -132,6 +132,21 @@ int ew_pick_tiled_dim(const EwPlan &plan) {
     return dS;
 }
 
+int ew_xpose_mode(const EwPlan &plan, int k, int dS, int m) {
+    const EwOperand &o = plan.op[k];
+    if (o.is_index) return 2;
+    const int64_t v = (int64_t)m * o.esize;  // vector bytes (<= 16)
+    auto aligned_elsewhere = [&](int unit_dim) {
+        if (((uintptr_t)o.ptr) % v != 0) return false;
+        for (int d = 0; d < plan.ndims; ++d)
+            if (d != unit_dim && (o.stride[d] * o.esize) % v != 0) return false;
+        return true;
+    };
+    if (o.stride[0] == 1 && aligned_elsewhere(0)) return 0;
+    if (o.stride[dS] == 1 && aligned_elsewhere(dS)) return 1;
+    return 2;
+}
+
 int ew_grid_for(int64_t work_items, int items_per_cta) {
     int64_t ctas = (work_items + items_per_cta - 1) / items_per_cta;
     // Enough CTAs to fill every SM several times over, few enough that launch overhead stays negligible;
