@@ -1,0 +1,583 @@
+// gemm.cu — MatMatDot / BatchedMatMatDot / MatVecDot / VecVecDot (Tensor/Tensor/TensorBackend.fs:137-140).
+//
+// Replaces the cuBLAS call sites of the reference (CudaBackend.fs:383-449, CudaBLAS.fs:17-64) and the operand
+// staging of BlasSupport.fs:148-190 (column-major temporaries + strided copy-back of every row-major result).
+//
+// float32 MatMatDot runs on the 5th-generation tensor cores: a persistent, warp-specialised tcgen05 kernel
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of A[128 x 32] and B[BN x 32] fp32 tiles (128-byte
+//               swizzle) into a multi-stage shared-memory ring, completion on mbarriers;
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) on
+//               shared-memory descriptors, fp32 accumulators live in TMEM (two stages, so the epilogue of tile i
+//               overlaps the main loop of tile i+1); tcgen05.commit releases smem slots / publishes accumulators;
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> row-major C written DIRECTLY with its
+//               own strides (the reference needs a column-major temp and a copy-back: BlasSupport.fs:181).
+// C = A·B with A[M,K] and B[K,N] given as arbitrary strided views: an operand whose K axis is contiguous and
+// TMA-aligned is consumed in place ("K-major"); anything else (an N-contiguous B, a transposed A, odd pitches) is
+// first repacked K-major by the element-wise transpose kernel (dn_copy) into stream-ordered scratch.
+// Inputs are read as TF32 (10-bit mantissa, the low 13 bits of the fp32 words are ignored by the tensor core),
+// accumulation is fp32: rel 1e-2 of the fp64 oracle per BASELINE.json north_star.
+// float64 has no tcgen05 path: a shared-memory tiled SIMT kernel.
+#include <cuda.h>
+
+#include "ew_ops.cuh"
+
+using namespace dn;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spin > (1u << 28)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 (unused for swizzled K-major) | SBO>>4 [32,46) = 1024 B (8 rows x 128 B)
+// | version = 1 [46,48) | layout_type = SWIZZLE_128B (2) [61,64)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+constexpr int kBM = 128;          // UMMA M
+constexpr int kBK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int kGemmThreads = 192; // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+
+struct GemmParams {
+    float *c;
+    int64_t ldc_m, ldc_n;  // element strides of C
+    int32_t M, N, K;
+    int32_t tiles_m, tiles_n;
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kStageBytes = (kBM + BN) * kBK * 4;
+    static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+    static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages, power of two >= 32
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                  const __grid_constant__ CUtensorMap map_b,
+                                                                  const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t *full = bars, *empty = bars + Cfg::kStages;
+    uint64_t *tmem_full = bars + 2 * Cfg::kStages, *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_kb = (p.K + kBK - 1) / kBK;
+
+    if (warp == 1 && elect_one()) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)Cfg::kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile % p.tiles_m, n_blk = tile / p.tiles_m;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t *sa = smem + stage * Cfg::kStageBytes;
+                    uint8_t *sb = sa + kBM * kBK * 4;
+                    mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+                    tma_load_2d(sa, &map_a, &full[stage], kb * kBK, m_blk * kBM);
+                    tma_load_2d(sb, &map_b, &full[stage], kb * kBK, n_blk * BN);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format TF32 (2) @7/@10,
+            // a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t sb = sa + kBM * kBK * 4;
+                    const uint64_t da = make_kmajor_sw128_desc(sa), db = make_kmajor_sw128_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < kBK / 8; ++k)  // UMMA K = 8 tf32 = 32 bytes: advance the start address
+                        umma_tf32(tmem_c, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty[stage]);
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // epilogue warps: TMEM lane quarter = warp % 4
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool vec_ok = p.ldc_n == 1 && (p.ldc_m % 4) == 0 && (reinterpret_cast<uintptr_t>(p.c) & 15) == 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile % p.tiles_m, n_blk = tile / p.tiles_m;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int row = m_blk * kBM + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int col = n_blk * BN + c0;
+                if (col >= p.N) break;  // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + (uint32_t)c0, r);
+                if (row < p.M) {
+                    float *crow = p.c + (int64_t)row * p.ldc_m + (int64_t)col * p.ldc_n;
+                    if (vec_ok && col + 32 <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(crow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col + j < p.N) crow[(int64_t)j * p.ldc_n] = __uint_as_float(r[j]);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side of the tf32 path
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 2-D fp32 tensor map over a K-major operand: rows x K, row pitch `pitch` elements; box = box_rows x 32.
+dn_status make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t K, int64_t pitch, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(DN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(DN_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return DN_OK;
+}
+
+// A 2-D operand view [rows, K] (element strides rs, ks).
+struct Operand2D {
+    const float *ptr;
+    int64_t rows, K, rs, ks;
+};
+
+bool tma_ready(const Operand2D &o) {
+    return o.ks == 1 && o.rs >= o.K && (o.rs % 4) == 0 && (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0;
+}
+
+// Repack into a fresh K-major buffer with a 16-byte aligned pitch (stream-ordered scratch).
+dn_status repack_kmajor(Operand2D &o, void **scratch) {
+    const int64_t pitch = (o.K + 3) / 4 * 4;
+    dn_status st = scratch_alloc((size_t)o.rows * pitch * 4, scratch);
+    if (st != DN_OK) return st;
+    dn_tensor src{}, dst{};
+    src.base = const_cast<float *>(o.ptr);
+    src.offset = 0;
+    src.ndims = 2;
+    src.dtype = DN_F32;
+    src.shape[0] = o.rows; src.shape[1] = o.K;
+    src.stride[0] = o.rs; src.stride[1] = o.ks;
+    dst = src;
+    dst.base = *scratch;
+    dst.stride[0] = pitch; dst.stride[1] = 1;
+    st = dn_copy(&dst, &src);
+    if (st != DN_OK) return st;
+    o.ptr = static_cast<const float *>(*scratch);
+    o.rs = pitch;
+    o.ks = 1;
+    return DN_OK;
+}
+
+template <int BN>
+dn_status launch_tf32(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p) {
+    using Cfg = GemmCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        DN_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        configured = true;
+    }
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    DN_LAUNCH((gemm_tf32_kernel<BN>), grid, kGemmThreads, Cfg::kSmemBytes, ma, mb, p);
+    return launch_status("tcgen05 GEMM kernel");
+}
+
+// C[M,N] (strides cm, cn) = A[M,K] (am, ak) · B[K,N] (bk, bn), fp32.
+dn_status gemm_f32(float *c, int64_t cm, int64_t cn, const float *a, int64_t am, int64_t ak, const float *b, int64_t bk,
+                   int64_t bn, int64_t M, int64_t N, int64_t K) {
+    if (M == 0 || N == 0) return DN_OK;
+    if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return set_error(DN_ERR_UNSUPPORTED, "MatMatDot: extent exceeds 2^31-1");
+    if (K == 0) {  // empty sum: C = 0
+        dn_tensor t{};
+        t.base = c; t.ndims = 2; t.dtype = DN_F32;
+        t.shape[0] = M; t.shape[1] = N; t.stride[0] = cm; t.stride[1] = cn;
+        const float zero = 0.f;
+        return dn_fill_const(&t, &zero);
+    }
+    Operand2D A{a, M, K, am, ak}, B{b, N, K, bn, bk};  // B viewed as [N, K]
+    void *sa = nullptr, *sb = nullptr;
+    dn_status st = DN_OK;
+    if (!tma_ready(A)) st = repack_kmajor(A, &sa);
+    if (st == DN_OK && !tma_ready(B)) st = repack_kmajor(B, &sb);
+    CUtensorMap ma, mb;
+    GemmParams p;
+    p.c = c; p.ldc_m = cm; p.ldc_n = cn;
+    p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K;
+    const int BN = N <= 32 ? 32 : (N <= 128 ? 128 : 256);
+    p.tiles_m = (int32_t)((M + kBM - 1) / kBM);
+    p.tiles_n = (int32_t)((N + BN - 1) / BN);
+    if (st == DN_OK) st = make_map(&ma, A.ptr, A.rows, K, A.rs, kBM);
+    if (st == DN_OK) st = make_map(&mb, B.ptr, B.rows, K, B.rs, BN);
+    if (st == DN_OK) {
+        if (BN == 32) st = launch_tf32<32>(ma, mb, p);
+        else if (BN == 128) st = launch_tf32<128>(ma, mb, p);
+        else st = launch_tf32<256>(ma, mb, p);
+    }
+    scratch_free(sa);
+    scratch_free(sb);
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// float64: shared-memory tiled SIMT kernel (64 x 64 tile, 4 x 4 per thread)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDT = 64, kDK = 16;
+
+__global__ void __launch_bounds__(256) gemm_f64_kernel(double *c, int64_t cm, int64_t cn, const double *a, int64_t am, int64_t ak,
+                                                      const double *b, int64_t bk, int64_t bn, int M, int N, int K) {
+    __shared__ double sa[kDK][kDT + 1], sb[kDK][kDT + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * kDT, n0 = blockIdx.x * kDT;
+    double acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += kDK) {
+        for (int i = threadIdx.x; i < kDT * kDK; i += 256) {
+            // choose the faster-varying index to follow the operand's contiguous axis
+            int mm, kk;
+            if (ak == 1) { kk = i % kDK; mm = i / kDK; } else { mm = i % kDT; kk = i / kDT; }
+            const int gm = m0 + mm, gk = k0 + kk;
+            sa[kk][mm] = (gm < M && gk < K) ? a[(int64_t)gm * am + (int64_t)gk * ak] : 0.0;
+            int nn, kb;
+            if (bk == 1) { kb = i % kDK; nn = i / kDK; } else { nn = i % kDT; kb = i / kDT; }
+            const int gn = n0 + nn, gk2 = k0 + kb;
+            sb[kb][nn] = (gn < N && gk2 < K) ? b[(int64_t)gk2 * bk + (int64_t)gn * bn] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kDK; ++kk) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { av[i] = sa[kk][ty * 4 + i]; bv[i] = sb[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+            if (gm < M && gn < N) c[(int64_t)gm * cm + (int64_t)gn * cn] = acc[i][j];
+        }
+}
+
+dn_status gemm_f64(double *c, int64_t cm, int64_t cn, const double *a, int64_t am, int64_t ak, const double *b, int64_t bk,
+                   int64_t bn, int64_t M, int64_t N, int64_t K) {
+    if (M == 0 || N == 0) return DN_OK;
+    if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return set_error(DN_ERR_UNSUPPORTED, "MatMatDot: extent exceeds 2^31-1");
+    dim3 grid((unsigned)((N + kDT - 1) / kDT), (unsigned)((M + kDT - 1) / kDT));
+    if (grid.y > 65535) return set_error(DN_ERR_UNSUPPORTED, "MatMatDot f64: M too large");
+    DN_LAUNCH(gemm_f64_kernel, grid, 256, 0, c, cm, cn, a, am, ak, b, bk, bn, (int)M, (int)N, (int)K);
+    return launch_status("f64 GEMM kernel");
+}
+
+dn_status check_mm(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b, int nd, const char *what) {
+    if (!tensor_valid(t) || !tensor_valid(a) || !tensor_valid(b)) return set_error(DN_ERR_INVALID_ARG, "%s: bad argument", what);
+    if (t->dtype != a->dtype || t->dtype != b->dtype) return set_error(DN_ERR_INVALID_ARG, "%s: operand types differ", what);
+    if (t->dtype != DN_F32 && t->dtype != DN_F64)
+        return set_error(DN_ERR_UNSUPPORTED, "%s is only supported for single and double (the reference falls back to "
+                                             "broadcast-multiply + sumAxis for other types on the host only)", what);
+    if (t->ndims != nd || a->ndims != nd || b->ndims != nd) return set_error(DN_ERR_SHAPE_MISMATCH, "%s: wrong rank", what);
+    if (a->shape[nd - 1] != b->shape[nd - 2] || t->shape[nd - 2] != a->shape[nd - 2] || t->shape[nd - 1] != b->shape[nd - 1])
+        return set_error(DN_ERR_SHAPE_MISMATCH, "%s: incompatible shapes", what);
+    for (int d = 0; d < nd - 2; ++d)
+        if (a->shape[d] != t->shape[d] || b->shape[d] != t->shape[d])
+            return set_error(DN_ERR_SHAPE_MISMATCH, "%s: batch dimensions differ", what);
+    return DN_OK;
+}
+
+dn_status mm_one(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b, int64_t to, int64_t ao, int64_t bo) {
+    const int nd = t->ndims;
+    const int64_t M = a->shape[nd - 2], K = a->shape[nd - 1], N = b->shape[nd - 1];
+    if (t->dtype == DN_F32)
+        return gemm_f32(reinterpret_cast<float *>(data_ptr(t)) + to, t->stride[nd - 2], t->stride[nd - 1],
+                        reinterpret_cast<const float *>(data_ptr(a)) + ao, a->stride[nd - 2], a->stride[nd - 1],
+                        reinterpret_cast<const float *>(data_ptr(b)) + bo, b->stride[nd - 2], b->stride[nd - 1], M, N, K);
+    return gemm_f64(reinterpret_cast<double *>(data_ptr(t)) + to, t->stride[nd - 2], t->stride[nd - 1],
+                    reinterpret_cast<const double *>(data_ptr(a)) + ao, a->stride[nd - 2], a->stride[nd - 1],
+                    reinterpret_cast<const double *>(data_ptr(b)) + bo, b->stride[nd - 2], b->stride[nd - 1], M, N, K);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// VecVecDot / MatVecDot: HBM-bound, one pass over the operands
+// ---------------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) dot_partial_kernel(const T *a, int64_t as, const T *b, int64_t bs, int64_t n, T *partials) {
+    T acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += a[i * as] * b[i * bs];
+    __shared__ T sm[8];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T s = 0;
+        for (int w = 0; w < 8; ++w) s += sm[w];
+        partials[blockIdx.x] = s;
+    }
+}
+template <class T>
+__global__ void dot_final_kernel(const T *partials, int n, T *out) {
+    T acc = 0;
+    for (int i = threadIdx.x; i < n; i += 32) acc += partials[i];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (threadIdx.x == 0) *out = acc;
+}
+
+// y[m] = sum_k A[m,k] x[k]; warp per row when k is the contiguous axis, thread per row otherwise.
+template <class T>
+__global__ void __launch_bounds__(256) matvec_kernel(T *y, int64_t ys, const T *a, int64_t am, int64_t ak, const T *x, int64_t xs,
+                                                    int64_t M, int64_t K, int warp_per_row) {
+    if (warp_per_row) {
+        const int lane = threadIdx.x & 31;
+        for (int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); m < M; m += (int64_t)gridDim.x * 8) {
+            T acc = 0;
+            for (int64_t k = lane; k < K; k += 32) acc += a[m * am + k * ak] * x[k * xs];
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+            if (lane == 0) y[m * ys] = acc;
+        }
+    } else {
+        for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+            T acc = 0;
+            for (int64_t k = 0; k < K; ++k) acc += a[m * am + k * ak] * x[k * xs];
+            y[m * ys] = acc;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+dn_status dn_mat_mat_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b) {
+    dn_status st = check_mm(t, a, b, 2, "MatMatDot");
+    if (st != DN_OK) return st;
+    return mm_one(t, a, b, 0, 0, 0);
+}
+
+dn_status dn_batched_mat_mat_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b) {
+    if (!tensor_valid(t) || t->ndims < 2) return set_error(DN_ERR_INVALID_ARG, "BatchedMatMatDot: bad argument");
+    const int nd = t->ndims;
+    dn_status st = check_mm(t, a, b, nd, "BatchedMatMatDot");
+    if (st != DN_OK) return st;
+    int64_t nbatch = 1;
+    for (int d = 0; d < nd - 2; ++d) nbatch *= t->shape[d];
+    for (int64_t bi = 0; bi < nbatch; ++bi) {
+        int64_t rem = bi, to = 0, ao = 0, bo = 0;
+        for (int d = nd - 3; d >= 0; --d) {
+            const int64_t x = rem % t->shape[d];
+            rem /= t->shape[d];
+            to += x * t->stride[d];
+            ao += x * a->stride[d];  // broadcast batch dims have stride 0
+            bo += x * b->stride[d];
+        }
+        st = mm_one(t, a, b, to, ao, bo);
+        if (st != DN_OK) return st;
+    }
+    return DN_OK;
+}
+
+dn_status dn_vec_vec_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b) {
+    if (!tensor_valid(t) || !tensor_valid(a) || !tensor_valid(b)) return set_error(DN_ERR_INVALID_ARG, "VecVecDot: bad argument");
+    if (t->ndims != 0 || a->ndims != 1 || b->ndims != 1 || a->shape[0] != b->shape[0])
+        return set_error(DN_ERR_SHAPE_MISMATCH, "VecVecDot: incompatible shapes");
+    if (t->dtype != a->dtype || t->dtype != b->dtype || (t->dtype != DN_F32 && t->dtype != DN_F64))
+        return set_error(DN_ERR_UNSUPPORTED, "VecVecDot is only supported for single and double");
+    const int64_t n = a->shape[0];
+    int grid = (int)((n + 2047) / 2048);
+    const int cap = sm_count() * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    void *scratch = nullptr;
+    dn_status st = scratch_alloc((size_t)grid * 8, &scratch);
+    if (st != DN_OK) return st;
+    if (t->dtype == DN_F32) {
+        DN_LAUNCH(dot_partial_kernel<float>, grid, 256, 0, (const float *)data_ptr(a), a->stride[0], (const float *)data_ptr(b),
+                  b->stride[0], n, (float *)scratch);
+        DN_LAUNCH(dot_final_kernel<float>, 1, 32, 0, (const float *)scratch, grid, (float *)data_ptr(t));
+    } else {
+        DN_LAUNCH(dot_partial_kernel<double>, grid, 256, 0, (const double *)data_ptr(a), a->stride[0], (const double *)data_ptr(b),
+                  b->stride[0], n, (double *)scratch);
+        DN_LAUNCH(dot_final_kernel<double>, 1, 32, 0, (const double *)scratch, grid, (double *)data_ptr(t));
+    }
+    scratch_free(scratch);
+    return launch_status("VecVecDot kernels");
+}
+
+dn_status dn_mat_vec_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b) {
+    if (!tensor_valid(t) || !tensor_valid(a) || !tensor_valid(b)) return set_error(DN_ERR_INVALID_ARG, "MatVecDot: bad argument");
+    if (t->ndims != 1 || a->ndims != 2 || b->ndims != 1 || a->shape[1] != b->shape[0] || t->shape[0] != a->shape[0])
+        return set_error(DN_ERR_SHAPE_MISMATCH, "MatVecDot: incompatible shapes");
+    if (t->dtype != a->dtype || t->dtype != b->dtype || (t->dtype != DN_F32 && t->dtype != DN_F64))
+        return set_error(DN_ERR_UNSUPPORTED, "MatVecDot is only supported for single and double");
+    const int64_t M = a->shape[0], K = a->shape[1];
+    if (M == 0) return DN_OK;
+    const int64_t abs_k = a->stride[1] < 0 ? -a->stride[1] : a->stride[1];
+    const int64_t abs_m = a->stride[0] < 0 ? -a->stride[0] : a->stride[0];
+    const int wpr = abs_k <= abs_m ? 1 : 0;
+    int64_t ctas = wpr ? (M + 7) / 8 : (M + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (ctas > cap) ctas = cap;
+    if (t->dtype == DN_F32)
+        DN_LAUNCH(matvec_kernel<float>, (unsigned)ctas, 256, 0, (float *)data_ptr(t), t->stride[0], (const float *)data_ptr(a),
+                  a->stride[0], a->stride[1], (const float *)data_ptr(b), b->stride[0], M, K, wpr);
+    else
+        DN_LAUNCH(matvec_kernel<double>, (unsigned)ctas, 256, 0, (double *)data_ptr(t), t->stride[0], (const double *)data_ptr(a),
+                  a->stride[0], a->stride[1], (const double *)data_ptr(b), b->stride[0], M, K, wpr);
+    return launch_status("MatVecDot kernel");
+}
+
+}  // extern "C"

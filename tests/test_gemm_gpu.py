@@ -1,0 +1,107 @@
+"""MatMatDot / BatchedMatMatDot / MatVecDot / VecVecDot parity against the fp64-accumulated oracle
+(host: MKL sgemm/dgemm, HostBackend.fs:463-546; reference tests: CudaTests.fs:54-75 `h .* i` GPU == host,
+BaseTests.fs:85-96 batched == per-sample loop). float32 runs on tcgen05 with TF32 inputs: tolerance rel 1e-2
+(north_star), measured norm-wise per row so that cancelling dot products are judged on the scale of their terms."""
+import numpy as np
+import pytest
+
+from deepnet_b200 import CudaTensor, Tensor, dtypes
+from helpers import pair, rand_array
+
+pytestmark = pytest.mark.gpu
+
+
+def check_mm(hc: Tensor, cc: Tensor, a: np.ndarray, b: np.ndarray, dtype: int, what: str):
+    h, c = hc.toNumpy().astype(np.float64), cc.toNumpy().astype(np.float64)
+    assert h.shape == c.shape, what
+    # scale of the terms of each dot product: |a| @ |b|
+    scale = np.abs(a.astype(np.float64)) @ np.abs(b.astype(np.float64))
+    tol = (2e-3 if dtype == dtypes.DN_F32 else 1e-13) * scale + 1e-30
+    err = np.abs(h - c)
+    assert (err <= tol).all(), f"{what}: max err/scale {np.max(err / (scale + 1e-30)):.3e}"
+    if dtype == dtypes.DN_F32 and h.size:
+        rel = np.linalg.norm(h - c) / (np.linalg.norm(h) + 1e-30)
+        assert rel <= 1e-2, f"{what}: norm-wise rel err {rel:.3e} > 1e-2"
+
+
+SHAPES = [(128, 256, 32), (128, 256, 64), (256, 512, 128), (5, 3, 3), (1, 1, 1), (130, 70, 45), (257, 300, 1000),
+          (1000, 10, 4096), (10, 4096, 1000), (512, 784, 64), (300, 33, 7), (64, 2048, 2048)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("dtype", [dtypes.DN_F32, dtypes.DN_F64])
+def test_mat_mat_dot_row_major(cuda_dev, M, N, K, dtype):
+    rng = np.random.default_rng(41)
+    a, b = rand_array(rng, (M, K), dtype, -1, 1), rand_array(rng, (K, N), dtype, -1, 1)
+    (ha, ca), (hb, cb) = pair(a), pair(b)
+    check_mm(ha @ hb, ca @ cb, a, b, dtype, f"{M}x{K} . {K}x{N}")
+
+
+@pytest.mark.parametrize("dtype", [dtypes.DN_F32, dtypes.DN_F64])
+def test_mat_mat_dot_layouts(cuda_dev, dtype):
+    """Every operand layout the MLP of config 5 produces: X·W.T, dY·W, dY.T·X, plus sliced / offset views and a
+    non-row-major target."""
+    rng = np.random.default_rng(42)
+    M, N, K = 192, 160, 136
+    a, bt = rand_array(rng, (M, K), dtype, -1, 1), rand_array(rng, (N, K), dtype, -1, 1)
+    (ha, ca), (hbt, cbt) = pair(a), pair(bt)
+    check_mm(ha @ hbt.T, ca @ cbt.T, a, bt.T, dtype, "A . B^T (both K-major)")
+    at = rand_array(rng, (K, M), dtype, -1, 1)
+    b = rand_array(rng, (K, N), dtype, -1, 1)
+    (hat, cat), (hb, cb) = pair(at), pair(b)
+    check_mm(hat.T @ hb, cat.T @ cb, at.T, b, dtype, "A^T . B (both MN-major)")
+    check_mm(ha @ hb, ca @ cb, a, b, dtype, "A . B")
+    check_mm(hat.T @ hbt.T, cat.T @ cbt.T, at.T, bt.T, dtype, "A^T . B^T")
+    # sliced views with odd offsets and pitches
+    check_mm(ha[3:131, 5:70] @ hb[5:70, 1:98], ca[3:131, 5:70] @ cb[5:70, 1:98], a[3:131, 5:70], b[5:70, 1:98], dtype,
+             "sliced")
+    # column-major target
+    ht = Tensor.empty((M, N), dtype, ha.Dev, order="F")
+    ct = Tensor.empty((M, N), dtype, ca.Dev, order="F")
+    ht.FillDot(ha, hb)
+    ct.FillDot(ca, cb)
+    check_mm(ht, ct, a, b, dtype, "column-major target")
+
+
+@pytest.mark.parametrize("dtype", [dtypes.DN_F32, dtypes.DN_F64])
+def test_batched_and_broadcast(cuda_dev, dtype):
+    """BaseTests.fs:85-114: batched matmul equals the per-sample loop; batch dims broadcast."""
+    rng = np.random.default_rng(43)
+    a, b = rand_array(rng, (3, 4, 70, 50), dtype, -1, 1), rand_array(rng, (3, 4, 50, 90), dtype, -1, 1)
+    (ha, ca), (hb, cb) = pair(a), pair(b)
+    hc, cc = ha @ hb, ca @ cb
+    assert cc.Shape == (3, 4, 70, 90)
+    for i in range(3):
+        for j in range(4):
+            check_mm(hc[i, j], cc[i, j], a[i, j], b[i, j], dtype, f"batch {i},{j}")
+            check_mm(hc[i, j], ca[i, j] @ cb[i, j], a[i, j], b[i, j], dtype, f"batch {i},{j} vs 2-D call")
+    b1 = rand_array(rng, (1, 1, 50, 90), dtype, -1, 1)
+    hb1, cb1 = pair(b1)
+    hc, cc = ha @ hb1, ca @ cb1
+    check_mm(hc[2, 3], cc[2, 3], a[2, 3], b1[0, 0], dtype, "broadcast batch")
+
+
+@pytest.mark.parametrize("dtype", [dtypes.DN_F32, dtypes.DN_F64])
+def test_vec_dots(cuda_dev, dtype):
+    rng = np.random.default_rng(44)
+    a, x, y = rand_array(rng, (300, 1000), dtype, -1, 1), rand_array(rng, (1000,), dtype, -1, 1), \
+        rand_array(rng, (1000,), dtype, -1, 1)
+    (ha, ca), (hx, cx), (hy, cy) = pair(a), pair(x), pair(y)
+    tol = 1e-4 if dtype == dtypes.DN_F32 else 1e-12
+    s_h, s_c = float((hx @ hy).Value), float((cx @ cy).Value)
+    assert abs(s_h - s_c) <= tol * float(np.abs(x.astype(np.float64)) @ np.abs(y.astype(np.float64)))
+    for (hm, cm, an) in [(ha, ca, a), (ha[10:200, :], ca[10:200, :], a[10:200, :])]:
+        hv, cv = (hm @ hx).toNumpy().astype(np.float64), (cm @ cx).toNumpy().astype(np.float64)
+        scale = np.abs(an.astype(np.float64)) @ np.abs(x.astype(np.float64))
+        assert (np.abs(hv - cv) <= tol * scale).all()
+    at = rand_array(rng, (1000, 300), dtype, -1, 1)
+    hat, cat = pair(at)
+    hv, cv = (hat.T @ hx).toNumpy().astype(np.float64), (cat.T @ cx).toNumpy().astype(np.float64)
+    assert (np.abs(hv - cv) <= tol * (np.abs(at.T.astype(np.float64)) @ np.abs(x.astype(np.float64)))).all()
+
+
+def test_unsupported_types(cuda_dev):
+    from deepnet_b200.native import NotSupportedException
+    a = CudaTensor.zeros((4, 4), dtypes.DN_I32)
+    with pytest.raises(NotSupportedException):
+        a @ a
