@@ -45,7 +45,7 @@ same("whole argmax", sh.reduce_axis("ArgMaxLastAxis", loc.flatten(), 0, R * C), 
 got = sh.reduce_axis("SumLastAxis", loc[:, 10:], 1, R).toNumpy(); want = full[:, 10:].sumAxis(1).toNumpy()
 if not np.allclose(got, want, rtol=1e-3, atol=1e-1): bad.append("sum axis 1")
 dist.barrier()
-print(f"RANK{rank}", "OK" if not bad else "FAIL " + ";".join(bad), flush=True)
+sys.stdout.write(f"RANK{rank}_" + ("OK" if not bad else "FAIL " + ";".join(bad)) + "\n"); sys.stdout.flush()
 dist.destroy_process_group()
 '''
 
@@ -60,4 +60,4 @@ def test_sharded_reductions_two_gpus(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
                          env=env, capture_output=True, text=True, timeout=600)
-    assert "RANK0 OK" in out.stdout and "RANK1 OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "RANK0_OK" in out.stdout and "RANK1_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
