@@ -55,6 +55,17 @@ dn_status red_make_plan(RedPlan &plan, const dn_tensor *t, const dn_tensor *a, c
     return DN_OK;
 }
 
+bool red_cols_can_vectorize(const RedPlan &plan, int vec) {
+    if (vec <= 1 || plan.nouter < 1) return false;
+    if (plan.ostride_s[0] != 1 || plan.oshape[0] % vec != 0) return false;
+    const int64_t align = (int64_t)vec * plan.in_size;  // <= 16
+    if (reinterpret_cast<uintptr_t>(plan.src) % align != 0) return false;
+    if ((plan.lstride_elems * plan.in_size) % align != 0) return false;
+    for (int d = 1; d < plan.nouter; ++d)
+        if ((plan.ostride_s[d] * plan.in_size) % align != 0) return false;
+    return true;
+}
+
 void red_fill_outer(RedOuter &o, const RedPlan &plan) {
     o.ndims = plan.nouter;
     for (int d = 0; d < DN_MAX_DIMS; ++d) {

@@ -152,6 +152,8 @@ struct MinMaxFloatOp {
     }
     __device__ static T neutral() { return IsMax ? -pos_inf() : pos_inf(); }
     __device__ static bool better(T a, T b) { return IsMax ? a > b : a < b; }  // `res > v` / `res < v`
+    // NaN-free operands only: one FMNMX; equals the host's pick in value (the sign of a +0/-0 tie may differ)
+    __device__ static T pick(T a, T b) { return IsMax ? fmax(a, b) : fmin(a, b); }
     __device__ static State identity() { return State{neutral(), 0}; }
     // exact sequential step (ScalarOps.fs:620-628): if res `better` v then res else v
     __device__ static void step(State &s, T v, int64_t) {
@@ -243,6 +245,9 @@ __device__ __forceinline__ typename Op::State warp_combine_unordered(typename Op
 // rows family
 // ---------------------------------------------------------------------------------------------------------------
 // One warp folds elements [begin, end) of a contiguous row. All lanes return the same state.
+// Structure: scalar head up to 16-byte alignment, then rounds of 32*VEC consecutive elements (lane l owns VEC
+// consecutive elements of a round), UNR rounds loaded before any is folded; the last group is the same code with
+// per-lane predicates (vector loads where a whole vector is in range, scalar loads for the final < VEC elements).
 template <class Op>
 __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const char *row, int64_t begin,
                                                             int64_t end, int lane) {
@@ -255,28 +260,36 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
     int64_t last_nan = -1;  // ordered ops only: index of the last NaN seen by the WARP (uniform)
     const T *p = reinterpret_cast<const T *>(row);
 
-    // one "round": lane handles n (<= VEC) consecutive elements starting at index i0 (or nothing if n == 0)
+    // fold one round: this lane holds n (0..VEC) consecutive elements starting at index i0
     auto round = [&](const T *v, int n, int64_t i0) {
         if constexpr (Op::ordered) {
-            int64_t my_nan = -1;
+            // cheap NaN probe: the sum of the lane's elements is NaN iff one of them is (or +inf meets -inf, a
+            // false positive that the exact slow path below resolves)
+            T probe = T(0);
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
-                if (j < n && v[j] != v[j]) my_nan = i0 + j;
-            if (__any_sync(kFull, my_nan >= 0)) {  // rare: a NaN in this round resets every lane
+                if (j < n) probe += v[j];
+            if (__any_sync(kFull, probe != probe)) {  // rare
+                int64_t my_nan = -1;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    if (j < n && v[j] != v[j]) my_nan = i0 + j;
 #pragma unroll
                 for (int m = 16; m >= 1; m >>= 1) {
-                    int64_t o = __shfl_xor_sync(kFull, my_nan, m);
+                    const int64_t o = __shfl_xor_sync(kFull, my_nan, m);
                     my_nan = o > my_nan ? o : my_nan;
                 }
-                last_nan = my_nan;
-                st.val = Op::neutral();
+                if (my_nan >= 0) {  // a real NaN in this round resets every lane
+                    last_nan = my_nan;
+                    st.val = Op::neutral();
+                }
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
                     if (j < n && i0 + j > last_nan) st.val = Op::better(st.val, v[j]) ? st.val : v[j];
             } else {
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
-                    if (j < n) st.val = Op::better(st.val, v[j]) ? st.val : v[j];
+                    if (j < n) st.val = Op::pick(st.val, v[j]);
             }
         } else {
 #pragma unroll
@@ -287,7 +300,6 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
 
     int64_t i = begin;
     if (i < end) {
-        // scalar head up to 16-byte alignment
         const uintptr_t addr = reinterpret_cast<uintptr_t>(p + i);
         int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
         if (head > end - i) head = (int)(end - i);
@@ -298,34 +310,46 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
             round(v, on ? 1 : 0, i + lane);
             i += head;
         }
-        // vector body, UNR rounds in flight
-        for (; i + (int64_t)ROUND * UNR <= end; i += (int64_t)ROUND * UNR) {
+        // groups of UNR rounds; only the last group of a part can be partial (per-lane predicates, scalar loads for
+        // the final < VEC elements); offsets inside a group are 32-bit
+        for (; i < end; i += (int64_t)ROUND * UNR) {
+            const int64_t rem64 = end - i;
+            const int rem = rem64 > (int64_t)ROUND * UNR ? ROUND * UNR : (int)rem64;  // elements left in this group
+            const T *g = p + i;
             Pack<T, VEC> buf[UNR];
+            if (rem == ROUND * UNR) {  // full group: UNR unconditional 128-bit loads back to back
 #pragma unroll
-            for (int u = 0; u < UNR; ++u)
-                buf[u] = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(p + i + (int64_t)u * ROUND + lane * VEC));
+                for (int u = 0; u < UNR; ++u)
+                    buf[u] = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(g + u * ROUND + lane * VEC));
+            } else {
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) round(buf[u].v, VEC, i + (int64_t)u * ROUND + lane * VEC);
-        }
-        for (; i + ROUND <= end; i += ROUND) {
-            Pack<T, VEC> b = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(p + i + lane * VEC));
-            round(b.v, VEC, i + lane * VEC);
-        }
-        // tail: < ROUND elements, VEC rounds of scalar loads keep index order across rounds
-        for (; i < end; i += 32) {
-            T v[VEC];
-            const bool on = i + lane < end;
-            if (on) v[0] = p[i + lane];
-            round(v, on ? 1 : 0, i + lane);
+                for (int u = 0; u < UNR; ++u) {
+                    const int off = u * ROUND + lane * VEC;
+                    if (off + VEC <= rem) {
+                        buf[u] = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(g + off));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j)
+                            if (off + j < rem) buf[u].v[j] = g[off + j];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int off = u * ROUND + lane * VEC;
+                if (u * ROUND < rem) {  // warp-uniform
+                    const int left = rem - off;
+                    round(buf[u].v, left >= VEC ? VEC : (left > 0 ? left : 0), i + off);
+                }
+            }
         }
     }
     if constexpr (Op::ordered) {
-        // lane values -> warp value; NaN bookkeeping is already warp-uniform
         T v = st.val;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
-            T o = __shfl_xor_sync(kFull, v, m);
-            v = Op::better(v, o) ? v : o;
+            const T o = __shfl_xor_sync(kFull, v, m);
+            v = Op::pick(v, o);
         }
         State out;
         out.flags = (end > begin ? 2 : 0) | (last_nan >= 0 ? 1 : 0);
@@ -397,49 +421,61 @@ __global__ void __launch_bounds__(kRedThreads) reduce_finalize_kernel(const __gr
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kColsTX = 32;
 
-template <class Op>
+// VEC > 1: the innermost outer dim is contiguous in the source (stride 1), its extent is a multiple of VEC and
+// everything is 16-byte aligned, so a thread owns VEC adjacent outputs and reads them with one 128-bit load per
+// step of the reduced axis (4 steps in flight).
+template <class Op, int VEC>
 __global__ void __launch_bounds__(kRedThreads) reduce_cols_kernel(const __grid_constant__ RedParams p, const Op op) {
     using T = typename Op::In;
     using State = typename Op::State;
     using Out = typename Op::Out;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    State *sm = reinterpret_cast<State *>(smem_raw);  // [blockDim.y][blockDim.x]
-    const uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    State *sm = reinterpret_cast<State *>(smem_raw);  // [blockDim.y][blockDim.x][VEC]
+    const uint64_t o0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;  // first output of this thread
     const int chunk = blockIdx.y * blockDim.y + threadIdx.y;
-    State st = Op::identity();
+    State st[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) st[j] = Op::identity();
     int64_t soff = 0, toff = 0;
-    const bool active = o < p.nrows;
+    const bool active = o0 < p.nrows;
     if (active) {
-        red_offsets(p.outer, (uint32_t)o, soff, toff);
+        red_offsets(p.outer, (uint32_t)o0, soff, toff);
         int64_t b = (int64_t)chunk * p.part_len, e = b + p.part_len;
         if (e > p.len) e = p.len;
         const char *q = p.src + soff + b * p.lstride;
         int64_t i = b;
         for (; i + 4 <= e; i += 4) {
-            T v0 = *reinterpret_cast<const T *>(q);
-            T v1 = *reinterpret_cast<const T *>(q + p.lstride);
-            T v2 = *reinterpret_cast<const T *>(q + 2 * p.lstride);
-            T v3 = *reinterpret_cast<const T *>(q + 3 * p.lstride);
+            Pack<T, VEC> v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = load_pack<Pack<T, VEC>>(q + u * p.lstride);
             q += 4 * p.lstride;
-            op_step(op, st, v0, i);
-            op_step(op, st, v1, i + 1);
-            op_step(op, st, v2, i + 2);
-            op_step(op, st, v3, i + 3);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) op_step(op, st[j], v[u].v[j], i + u);
         }
         for (; i < e; ++i) {
-            op_step(op, st, *reinterpret_cast<const T *>(q), i);
+            const Pack<T, VEC> v = load_pack<Pack<T, VEC>>(q);
             q += p.lstride;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) op_step(op, st[j], v.v[j], i);
         }
     }
     if (blockDim.y > 1) {
-        sm[threadIdx.y * blockDim.x + threadIdx.x] = st;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) sm[(threadIdx.y * blockDim.x + threadIdx.x) * VEC + j] = st[j];
         __syncthreads();
         if (threadIdx.y != 0) return;
-        for (int y = 1; y < (int)blockDim.y; ++y) st = Op::combine(st, sm[y * blockDim.x + threadIdx.x]);
+        for (int y = 1; y < (int)blockDim.y; ++y)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) st[j] = Op::combine(st[j], sm[(y * blockDim.x + threadIdx.x) * VEC + j]);
     }
     if (!active) return;
-    if (gridDim.y == 1) *reinterpret_cast<Out *>(p.dst + toff) = Op::finalize(st);
-    else reinterpret_cast<State *>(p.partials)[o * gridDim.y + blockIdx.y] = st;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        if (gridDim.y == 1) *reinterpret_cast<Out *>(p.dst + toff + j * p.outer.tstride[0]) = Op::finalize(st[j]);
+        else reinterpret_cast<State *>(p.partials)[(o0 + j) * gridDim.y + blockIdx.y] = st[j];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -459,6 +495,8 @@ struct RedPlan {
 // merge). nrows == 0 means nothing to do.
 dn_status red_make_plan(RedPlan &plan, const dn_tensor *t, const dn_tensor *a, const char *what);
 void red_fill_outer(RedOuter &o, const RedPlan &plan);
+// True when a thread of the cols family may own `vec` adjacent outputs and read them with one vector load.
+bool red_cols_can_vectorize(const RedPlan &plan, int vec);
 
 template <class Op>
 dn_status red_run(const RedPlan &plan, const Op &op) {
@@ -486,7 +524,12 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
         if (rows_family) {
             const int64_t warps_wanted = (int64_t)sms * 32;  // enough resident warps to cover HBM latency
             const int64_t bytes = L * plan.in_size;
-            if (rc >= warps_wanted / 4 || bytes <= 8192) {
+            // short rows: a warp per row (one or two load groups cover the row). Long rows: a CTA per row, so that
+            // a row's latency chain is 1/8 as long and small row counts still fill the machine.
+            // (measured: with >= one warp per resident slot and rows <= 64 KiB, the state-heavy ops — ordered
+            // float Min/Max, (value, index) pairs — run faster warp-per-row; plain folds prefer CTA-per-row)
+            const bool heavy = Op::ordered || sizeof(State) > 8;
+            if (bytes <= 4096 || (heavy && rc >= warps_wanted && bytes <= 65536)) {
                 p.parts = 1;
                 p.part_len = L;
                 int64_t ctas = (rc + kRedWarps - 1) / kRedWarps;
@@ -524,15 +567,18 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
         } else {
             // cols family: TX threads along outputs; TY*GY chunks along the axis when outputs alone cannot fill
             // the machine.
+            constexpr int kColsVec = 16 / (int)sizeof(typename Op::In) > 4 ? 4 : 16 / (int)sizeof(typename Op::In);
+            const int vec = red_cols_can_vectorize(plan, kColsVec) ? kColsVec : 1;
             int tx = kColsTX, ty = kRedThreads / kColsTX;
-            int64_t gx = (rc + tx - 1) / tx;
+            const int64_t threads_x = (rc + vec - 1) / vec;
+            int64_t gx = (threads_x + tx - 1) / tx;
             int64_t gy = 1;
             if (L < 64) {  // short axis: no point in splitting it
                 tx = kRedThreads;
                 ty = 1;
-                gx = (rc + tx - 1) / tx;
-            } else if (gx < 2 * sms) {
-                gy = (2 * (int64_t)sms + gx - 1) / gx;
+                gx = (threads_x + tx - 1) / tx;
+            } else if (gx < 4 * sms) {
+                gy = (4 * (int64_t)sms + gx - 1) / gx;
                 const int64_t max_gy = L / (ty * 64) > 0 ? L / (ty * 64) : 1;
                 if (gy > max_gy) gy = max_gy;
                 if (gy > 65535) gy = 65535;
@@ -547,8 +593,11 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
                 if (st != DN_OK) return st;
                 p.partials = scratch;
             }
-            const size_t smem = ty > 1 ? (size_t)tx * ty * sizeof(State) : 0;
-            DN_LAUNCH((reduce_cols_kernel<Op>), dim3((unsigned)gx, (unsigned)gy), dim3(tx, ty), smem, p, op);
+            const size_t smem = ty > 1 ? (size_t)tx * ty * sizeof(State) * vec : 0;
+            if (vec > 1)
+                DN_LAUNCH((reduce_cols_kernel<Op, kColsVec>), dim3((unsigned)gx, (unsigned)gy), dim3(tx, ty), smem, p, op);
+            else
+                DN_LAUNCH((reduce_cols_kernel<Op, 1>), dim3((unsigned)gx, (unsigned)gy), dim3(tx, ty), smem, p, op);
             if (gy > 1) {
                 DN_LAUNCH((reduce_finalize_kernel<Op>), (unsigned)((rc + kRedThreads - 1) / kRedThreads),
                           kRedThreads, 0, p);
