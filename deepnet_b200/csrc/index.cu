@@ -276,6 +276,33 @@ __device__ __forceinline__ uint32_t load_mask_bits(const BoolView &m, uint32_t f
 __global__ void __launch_bounds__(kIdxThreads) mask_count_kernel(const __grid_constant__ BoolView m, uint32_t *tile_counts,
                                                               unsigned long long *total) {
     __shared__ uint32_t warp_sums[kIdxThreads / 32];
+    if (!tile_counts) {
+        // count only (dn_count_true): keep several 128-bit loads in flight, one block reduction at the very end
+        unsigned long long acc = 0;
+        const uint64_t nchunks = ((uint64_t)m.n + kItems - 1) / kItems;
+        for (uint64_t c = (uint64_t)blockIdx.x * kIdxThreads + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * kIdxThreads * 4) {
+            uint32_t b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t cc = c + (uint64_t)u * gridDim.x * kIdxThreads;
+                b[u] = cc < nchunks ? load_mask_bits(m, (uint32_t)(cc * kItems)) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += __popc(b[u]);
+        }
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        __shared__ unsigned long long wsum[kIdxThreads / 32];
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+#pragma unroll
+            for (int w = 0; w < kIdxThreads / 32; ++w) t += wsum[w];
+            if (t) atomicAdd(total, t);
+        }
+        return;
+    }
     for (uint32_t tile = blockIdx.x; (uint64_t)tile * kTileElems < m.n; tile += gridDim.x) {
         const uint32_t f0 = tile * kTileElems + threadIdx.x * kItems;
         uint32_t c = __popc(load_mask_bits(m, f0));
@@ -287,8 +314,7 @@ __global__ void __launch_bounds__(kIdxThreads) mask_count_kernel(const __grid_co
             uint32_t t = 0;
 #pragma unroll
             for (int w = 0; w < kIdxThreads / 32; ++w) t += warp_sums[w];
-            if (tile_counts) tile_counts[tile] = t;
-            if (total && t) atomicAdd(total, (unsigned long long)t);
+            tile_counts[tile] = t;
         }
         __syncthreads();
     }
@@ -390,6 +416,7 @@ template <class Sink>
 __global__ void __launch_bounds__(kIdxThreads) mask_emit_kernel(const __grid_constant__ BoolView m, const int64_t *tile_offsets,
                                                              const Sink sink) {
     __shared__ uint32_t warp_sums[kIdxThreads / 32];
+    __shared__ uint32_t staged[kTileElems];  // logical positions of the tile's true elements, in order
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t tile = blockIdx.x; (uint64_t)tile * kTileElems < m.n; tile += gridDim.x) {
         const uint32_t f0 = tile * kTileElems + threadIdx.x * kItems;
@@ -403,17 +430,23 @@ __global__ void __launch_bounds__(kIdxThreads) mask_emit_kernel(const __grid_con
         }
         if (lane == 31) warp_sums[warp] = incl;
         __syncthreads();
-        uint32_t before = 0;
+        uint32_t before = 0, tile_total = 0;
 #pragma unroll
-        for (int w = 0; w < kIdxThreads / 32; ++w)
+        for (int w = 0; w < kIdxThreads / 32; ++w) {
             if (w < warp) before += warp_sums[w];
-        int64_t rank = tile_offsets[tile] + before + incl - c;
+            tile_total += warp_sums[w];
+        }
+        uint32_t local = before + incl - c;
         uint32_t b = bits;
         while (b) {
             const int j = __ffs(b) - 1;
             b &= b - 1;
-            sink(rank++, f0 + j);
+            staged[local++] = f0 + j;
         }
+        __syncthreads();
+        // consecutive threads emit consecutive ranks: dense-side accesses are fully coalesced
+        const int64_t base = tile_offsets[tile];
+        for (uint32_t i = threadIdx.x; i < tile_total; i += kIdxThreads) sink(base + i, staged[i]);
         __syncthreads();
     }
 }
