@@ -78,7 +78,9 @@ def build_cases(T, dt, a, b, c, row, col, mask, has_sin: bool):
 
 def dtype_list():
     from deepnet_b200 import dtypes
-    return [(dtypes.DN_F32, np.float32, True), (dtypes.DN_F64, np.float64, True), (dtypes.DN_I32, np.int32, False)]
+    # third field: use sin as the unary case. float64 sin is FP64-compute-bound on B200 (reported under
+    # other_configs), so the HBM metric uses abs on the transposed view for float64 and int32.
+    return [(dtypes.DN_F32, np.float32, True), (dtypes.DN_F64, np.float64, False), (dtypes.DN_I32, np.int32, False)]
 
 
 def host_inputs(rng, side, npdt):
@@ -93,25 +95,50 @@ def host_inputs(rng, side, npdt):
 # clocks sampling (B200_PROFILING.md)
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Samples SM clocks and throttle reasons DURING the timed region (NVML; nvidia-smi as a fallback)."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.samples = []   # (sm_mhz, max_mhz, set(reasons))
         self._stop = threading.Event()
         self._thread = None
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not self._stop.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.samples.append((float(sm), float(mx), {n for n, b in bits.items() if r & b}))
+            self._stop.wait(0.01)
+
+    def _run_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
                 out = subprocess.check_output(
                     ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                     timeout=5).decode().strip()
-                self.samples.append([x.strip() for x in out.split(",")])
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append((float(f[0]), float(f[1]),
+                                     {n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")}))
             except Exception:
                 pass
             self._stop.wait(0.1)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def start(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -121,18 +148,10 @@ class ClockSampler:
         self._stop.set()
         if self._thread:
             self._thread.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                mx.append(float(s[1]))
-                for n, v in zip(names, s[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        sm = [s[0] for s in self.samples]
+        reasons = set().union(*[s[2] for s in self.samples]) if self.samples else set()
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(s[1] for s in self.samples) if self.samples else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -165,10 +184,110 @@ def run_cpu_cases(side: int, steps: int, warmup: int):
     return total_bytes / sec / 1e9, sec, total_bytes
 
 
+def measure_other_configs(dev, torch, peak):
+    """C1 / C3 / C4 / C5 of BASELINE.json measured once each on rank 0 (reported beside the headline, not part of it).
+    Every entry: median of 5 timings of `reps` back-to-back calls, CUDA events on the launching stream."""
+    from deepnet_b200 import CudaTensor, Tensor, dtypes
+    stream = torch.cuda.current_stream()
+    out = {}
+
+    def w(t, dt):
+        return CudaTensor.usingPtr(t.data_ptr(), tuple(t.shape), dt, owner=t)
+
+    def timed(fn, reps=4):
+        fn()
+        ts = []
+        for _ in range(5):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            for _ in range(reps):
+                fn()
+            e.record(stream)
+            e.synchronize()
+            ts.append(s.elapsed_time(e) / reps)
+        return statistics.median(ts)
+
+    def hbm(name, nbytes, fn, reps=4):
+        ms = timed(fn, reps)
+        out[name] = {"ms": round(ms, 4), "GB/s": round(nbytes / ms / 1e6, 1), "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
+
+    F32, I64, BOOL = dtypes.DN_F32, dtypes.DN_I64, dtypes.DN_BOOL
+    # C1: c = a*b + sin(a) over 2^24 elements as three backend calls, then SumLastAxis over 4096x4096
+    ta, tb = (torch.rand(4096, 4096, device="cuda") * 100 - 50 for _ in range(2))
+    a, b = w(ta, F32), w(tb, F32)
+    t1, t2, c = (Tensor.empty((4096, 4096), F32, dev) for _ in range(3))
+    o1 = Tensor.empty((4096,), F32, dev)
+    n1 = 4096 * 4096 * 4
+
+    def c1():
+        t1.FillMultiply(a, b)
+        t2.FillSin(a)
+        c.FillAdd(t1, t2)
+        o1.FillSumAxis(1, c)
+    hbm("C1 a*b+sin(a) (3 calls) + SumLastAxis 4096x4096 [small kernels: includes host launch gaps]", 9 * n1 + 4096 * 4, c1, 8)
+    td = torch.rand(8192, 8192, device="cuda", dtype=torch.float64) * 100 - 50
+    dd, dc = w(td, dtypes.DN_F64), Tensor.empty((8192, 8192), dtypes.DN_F64, dev)
+    hbm("float64 sin 8192x8192 (FP64-compute-bound on B200, not an HBM kernel)", 2 * 8 * 8192 * 8192, lambda: dc.FillSin(dd))
+    del td, dd, dc
+    # C3: ArgMaxLastAxis + MaxLastAxis over 262144 x 1000 float32
+    tl = torch.rand(262144, 1000, device="cuda") * 100 - 50
+    lg = w(tl, F32)
+    oi, om = Tensor.empty((262144,), I64, dev), Tensor.empty((262144,), F32, dev)
+    nb = 262144 * 1000 * 4
+    hbm("C3 ArgMaxLastAxis 262144x1000 f32", nb + 262144 * 8, lambda: oi._fill_axis("ArgMaxLastAxis", 1, lg, True))
+    hbm("C3 MaxLastAxis 262144x1000 f32", nb + 262144 * 4, lambda: om.FillMaxAxis(1, lg))
+    hbm("C3 SumLastAxis 262144x1000 f32", nb + 262144 * 4, lambda: om.FillSumAxis(1, lg))
+    del tl, lg
+    # C4: gather / scatter / masked get / trueIdx on 2^26 int64 / bool
+    N = 1 << 26
+    tsrc = torch.randint(-(1 << 40), 1 << 40, (N,), device="cuda", dtype=torch.int64)
+    tidx = torch.randint(0, N, (N,), device="cuda", dtype=torch.int64)
+    src, idx = w(tsrc, I64), w(tidx, I64)
+    trg = Tensor.empty((N,), I64, dev)
+    hbm("C4 Gather 2^26 int64 (random idx)", 3 * 8 * N, lambda: trg.FillGather([idx], src), 2)
+    hbm("C4 Scatter 2^26 int64 (random idx)", 5 * 8 * N, lambda: trg.FillScatter([idx], src), 2)
+    tmask = torch.rand(N, device="cuda") < 0.5
+    mask = w(tmask, BOOL)
+    ntrue = int(tmask.sum().item())
+    got = Tensor.empty((ntrue,), I64, dev)
+    hbm("C4 MaskedGet 2^26 int64 p=0.5", N + 8 * N + 8 * ntrue, lambda: src.Backend.MaskedGet(got, src, [mask]), 2)
+    hbm("C4 MaskedSet 2^26 int64 p=0.5", N + 16 * ntrue, lambda: trg.Backend.MaskedSet(trg, [mask], got), 2)
+    m2 = mask.reshape((8192, 8192))
+    ti = Tensor.empty((ntrue, 2), I64, dev)
+    hbm("C4 TrueIndices [8192,8192] p=0.5", N + 16 * ntrue, lambda: ti.Backend.TrueIndices(ti, m2), 2)
+    del tsrc, tidx, src, idx, trg, got, ti
+    # C5: MLP training step 784-4096-4096-10, batch 8192 (tcgen05 TF32 MatMatDot + element-wise + reductions)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from mlp_step import flops_per_step, init_params, synthetic_batch, train_step
+    sizes, batch = (784, 4096, 4096, 10), 8192
+    rng = np.random.default_rng(5)
+    params = [(CudaTensor.ofNumpy(wt), CudaTensor.ofNumpy(bs)) for wt, bs in init_params(rng, sizes)]
+    xn, tn = synthetic_batch(rng, batch, sizes[0], sizes[-1])
+    x, t = CudaTensor.ofNumpy(xn), CudaTensor.ofNumpy(tn)
+    ms = timed(lambda: train_step(x, t, params, 1e-3), 3)
+    fl = flops_per_step(batch, sizes)
+    out["C5 MLP 784-4096-4096-10 batch 8192 training step"] = {"ms": round(ms, 3), "TFLOP/s": round(fl / ms / 1e9, 1),
+                                                              "gemm_tflop_per_step": round(fl / 1e12, 3)}
+    # the GEMM alone (largest layer), against cuBLAS-free denominators: measured bf16 peak / 2 for tf32
+    th, tw = torch.randn(8192, 4096, device="cuda"), torch.randn(4096, 4096, device="cuda")
+    hh, ww, cc = w(th, F32), w(tw, F32), Tensor.empty((8192, 4096), F32, dev)
+    ms = timed(lambda: cc.FillDot(hh, ww.T), 5)
+    tf = 2.0 * 8192 * 4096 * 4096 / ms / 1e9
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            bf16 = float(json.load(f)["bf16_tflops"])
+    except Exception:
+        bf16 = 1590.0
+    out["C5 MatMatDot 8192x4096x4096 f32 (tcgen05 kind::tf32)"] = {
+        "ms": round(ms, 4), "TFLOP/s": round(tf, 1), "frac_of_tf32_peak": round(tf / (bf16 / 2), 3),
+        "tf32_peak_assumed": f"{bf16 / 2:.1f} = measured bf16 peak / 2"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--side", type=int, default=SIDE, help="tensor side (default 16384 = 2^28 elements)")
@@ -353,6 +472,13 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if world == 1 and not args.no_extra:
+        try:
+            del per_dtype, keep, pinned
+            torch.cuda.empty_cache()
+            line["other_configs"] = measure_other_configs(dev, torch, peak)
+        except Exception as ex:  # the side measurements must never take the headline down
+            line["other_configs"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         gbs, sec, nbytes = run_cpu_cases(args.cpu_side, 2, 1)
         line["cpu_baseline"] = {
