@@ -426,27 +426,58 @@ def main():
         h2d += sum(x.numel() * x.element_size() for x in hp)
         d2h += out.numel() * out.element_size()
     api = dev.api
+    # Three streams through the C ABI (dn_set_stream is per thread, switched around each group of calls): uploads
+    # of dtype k+1 overlap the kernels of dtype k and the download of dtype k-1. Ordering is by events
+    # (dn_event_record / dn_stream_wait_event); the step ends with dn_sync on every stream.
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    import ctypes as C
+
+    def mk_event():
+        e = C.c_void_p()
+        api.call("event_create", C.byref(e))
+        return e
+
+    ev_up = [mk_event() for _ in pinned]
+    ev_done = [mk_event() for _ in pinned]
+    ev_free = [mk_event() for _ in pinned]   # previous step's kernels done with a, b of this dtype
 
     def e2e_step():
-        for (dt, cases, (a, b, c)), (hp, out), (_, _, _) in zip(per_dtype, pinned, dtype_list()):
+        for k, ((dt, cases, (a, b, c)), (hp, out)) in enumerate(zip(per_dtype, pinned)):
             isz = dtypes.itemsize(dt)
-            # Transfer host->device through the C ABI (dn_memcpy_h2d, async on the stream from pinned memory)
+            dev.SetStream(s_h2d.cuda_stream)
+            api.call("stream_wait_event", ev_free[k])      # do not overwrite inputs still being read
             api.call("memcpy_h2d", a.Storage.BasePtr(), hp[0].data_ptr(), hp[0].numel() * isz)
             api.call("memcpy_h2d", b.Storage.BasePtr(), hp[1].data_ptr(), hp[1].numel() * isz)
+            api.call("event_record", ev_up[k])
+            dev.SetStream(stream.cuda_stream)
+            api.call("stream_wait_event", ev_up[k])
             for _, _, fn in cases:
                 fn()
-            api.call("memcpy_d2h", out.data_ptr(), c.Storage.BasePtr(), out.numel() * isz)
+            api.call("event_record", ev_done[k])
+            api.call("event_record", ev_free[k])
+            dev.SetStream(s_d2h.cuda_stream)
+            api.call("stream_wait_event", ev_done[k])
+            api.call("memcpy_d2h_async", out.data_ptr(), c.Storage.BasePtr(), out.numel() * isz)
+        # the step's results must be on the host before the step counts as finished
+        for st in (s_h2d, s_d2h):
+            dev.SetStream(st.cuda_stream)
+            dev.Synchronize()
+        dev.SetStream(stream.cuda_stream)
+        dev.Synchronize()
 
     e2e_steps = max(1, min(args.steps, 3))
+    for k in range(len(pinned)):
+        api.call("event_record", ev_free[k])
     e2e_step()
     barrier()
+    # several streams are involved, so the step is timed on the host between full synchronisations (every
+    # e2e_step ends with dn_sync on all three streams); max over ranks below
     t0 = time.perf_counter()
-    ev0.record(stream)
     for _ in range(e2e_steps):
         e2e_step()
-    ev1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     barrier()
-    e2e_ms = ev0.elapsed_time(ev1) / e2e_steps
     t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -261,6 +261,35 @@ dn_status dn_memcpy_d2h(void *dst_host, const void *src_dev, int64_t nbytes) {
     return DN_OK;
 }
 
+dn_status dn_memcpy_d2h_async(void *dst_host, const void *src_dev, int64_t nbytes) {
+    if (nbytes <= 0) return DN_OK;
+    DN_CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, (size_t)nbytes, cudaMemcpyDeviceToHost, t_stream));
+    return DN_OK;
+}
+
+dn_status dn_event_create(void **event) {
+    if (!event) return set_error(DN_ERR_INVALID_ARG, "dn_event_create: null argument");
+    cudaEvent_t e;
+    DN_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *event = e;
+    return DN_OK;
+}
+
+dn_status dn_event_destroy(void *event) {
+    if (event) DN_CUDA_TRY(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+    return DN_OK;
+}
+
+dn_status dn_event_record(void *event) {
+    DN_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(event), t_stream));
+    return DN_OK;
+}
+
+dn_status dn_stream_wait_event(void *event) {
+    DN_CUDA_TRY(cudaStreamWaitEvent(t_stream, static_cast<cudaEvent_t>(event), 0));
+    return DN_OK;
+}
+
 dn_status dn_memcpy_d2d(void *dst_dev, const void *src_dev, int64_t nbytes) {
     if (nbytes <= 0) return DN_OK;
     DN_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_dev, (size_t)nbytes, cudaMemcpyDeviceToDevice, t_stream));

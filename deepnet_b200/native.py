@@ -118,6 +118,11 @@ _DEVICE_SIGNATURES = {
     "memcpy_h2d": [C.c_void_p, C.c_void_p, C.c_int64],
     "memcpy_d2h": [C.c_void_p, C.c_void_p, C.c_int64],
     "memcpy_d2d": [C.c_void_p, C.c_void_p, C.c_int64],
+    "memcpy_d2h_async": [C.c_void_p, C.c_void_p, C.c_int64],
+    "event_create": [C.POINTER(C.c_void_p)],
+    "event_destroy": [C.c_void_p],
+    "event_record": [C.c_void_p],
+    "stream_wait_event": [C.c_void_p],
     "get_item": [_P, C.POINTER(C.c_int64), C.c_void_p],
     "set_item": [_P, C.POINTER(C.c_int64), C.c_void_p],
     "arg_reduce_combine": [C.c_int32, _P, _P, _P],

@@ -130,6 +130,16 @@ dn_status dn_memset_zero(void *ptr, int64_t nbytes);
 dn_status dn_memcpy_h2d(void *dst_dev, const void *src_host, int64_t nbytes);
 dn_status dn_memcpy_d2h(void *dst_host, const void *src_dev, int64_t nbytes);
 dn_status dn_memcpy_d2d(void *dst_dev, const void *src_dev, int64_t nbytes);
+/* Same as dn_memcpy_d2h but does not wait: the host buffer (pinned) is valid after dn_sync() on the same stream.
+ * This is the `Cfg.Stream <> NullStream` branch of Transfer (CudaBackend.fs:243-247, AsyncCopyFromDevice). */
+dn_status dn_memcpy_d2h_async(void *dst_host, const void *src_dev, int64_t nbytes);
+/* Stream ordering helpers for callers that overlap transfers with compute on several streams: record an event on
+ * the calling thread's stream / make the calling thread's stream wait for it. Events are created by dn_event_create
+ * and are opaque. */
+dn_status dn_event_create(void **event);
+dn_status dn_event_destroy(void *event);
+dn_status dn_event_record(void *event);
+dn_status dn_stream_wait_event(void *event);
 /* ITensorBackend.Item get/set (CudaBackend.fs:77-93,199-201): synchronous single-element access; `pos` has
  * t->ndims entries; `value` points to one element of t->dtype. */
 dn_status dn_get_item(const dn_tensor *t, const int64_t *pos, void *value);
