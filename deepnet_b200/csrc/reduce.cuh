@@ -211,6 +211,9 @@ struct ArgOp {
     __device__ static Out finalize(State s) { return s.idx; }
 };
 
+template <class Op> struct IsArgOp : std::false_type {};
+template <class T, bool IsMax> struct IsArgOp<ArgOp<T, IsMax>> : std::true_type {};
+
 template <class T>
 struct FindOp {
     using In = T; using Out = int64_t; using State = int64_t;
@@ -258,6 +261,7 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
     constexpr int UNR = 4;
     State st = Op::identity();
     int64_t last_nan = -1;  // ordered ops only: index of the last NaN seen by the WARP (uniform)
+    int ridx = -1;          // arg ops only: lane-local best index relative to `begin`
     const T *p = reinterpret_cast<const T *>(row);
 
     // fold one round: this lane holds n (0..VEC) consecutive elements starting at index i0
@@ -291,6 +295,16 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
                 for (int j = 0; j < VEC; ++j)
                     if (j < n) st.val = Op::pick(st.val, v[j]);
             }
+        } else if constexpr (IsArgOp<Op>::value) {
+            // (value, index) pairs: the lane tracks a 32-bit index relative to `begin` (one select instead of a
+            // 64-bit pair per element); it is widened once at the end of the part
+            const int r0 = (int)(i0 - begin);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                if (j < n && Op::better(v[j], st.val)) {
+                    st.val = v[j];
+                    ridx = r0 + j;
+                }
         } else {
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
@@ -357,6 +371,8 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
         if (last_nan >= 0 && last_nan == end - 1) out.val = p[last_nan];  // piece ends with the NaN itself
         return out;
     } else {
+        if constexpr (IsArgOp<Op>::value)
+            if (ridx >= 0) st.idx = begin + ridx;
         return warp_combine_unordered<Op>(st);
     }
 }
