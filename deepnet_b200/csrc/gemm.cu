@@ -103,6 +103,17 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// MN-major tf32 operands: the only shared-memory layout UMMA accepts is the 128-byte swizzle with a 32-byte atom
+// (layout_type 1, cute Swizzle<2,5,2>; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B). The tile is stored as
+// (MN extent / 32) consecutive blocks of [32 k-rows x 128 B], each row holding 32 consecutive MN elements — exactly
+// what a TMA box {32 MN, 32 K} writes. Canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units:
+// LBO = one block = 4096 B, SBO = one 4-row k-group = 512 B. One tf32 MMA (K = 8) consumes two k-groups, so the
+// start address advances by 1024 B per k-step.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           (1ull << 46) | (1ull << 61);
+}
+
 constexpr int kBM = 128;          // UMMA M
 constexpr int kBK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int kGemmThreads = 192; // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
@@ -122,7 +133,8 @@ struct GemmCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// A_MN / B_MN: the operand is MN-major (its M resp. N axis is the contiguous one) and is consumed in place.
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_b,
                                                                   const GemmParams p) {
@@ -170,8 +182,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_kernel(const __grid
                     uint8_t *sa = smem + stage * Cfg::kStageBytes;
                     uint8_t *sb = sa + kBM * kBK * 4;
                     mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-                    tma_load_2d(sa, &map_a, &full[stage], kb * kBK, m_blk * kBM);
-                    tma_load_2d(sb, &map_b, &full[stage], kb * kBK, n_blk * BN);
+                    if constexpr (A_MN) {
+#pragma unroll
+                        for (int blk = 0; blk < kBM / 32; ++blk)  // box {32 M, 32 K}: coordinates (m, k)
+                            tma_load_2d(sa + blk * 4096, &map_a, &full[stage], m_blk * kBM + blk * 32, kb * kBK);
+                    } else {
+                        tma_load_2d(sa, &map_a, &full[stage], kb * kBK, m_blk * kBM);
+                    }
+                    if constexpr (B_MN) {
+#pragma unroll
+                        for (int blk = 0; blk < BN / 32; ++blk)
+                            tma_load_2d(sb + blk * 4096, &map_b, &full[stage], n_blk * BN + blk * 32, kb * kBK);
+                    } else {
+                        tma_load_2d(sb, &map_b, &full[stage], kb * kBK, n_blk * BN);
+                    }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -180,7 +204,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_kernel(const __grid
         if (elect_one()) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format TF32 (2) @7/@10,
             // a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -194,10 +219,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_kernel(const __grid
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
                     const uint32_t sb = sa + kBM * kBK * 4;
-                    const uint64_t da = make_kmajor_sw128_desc(sa), db = make_kmajor_sw128_desc(sb);
+                    const uint64_t da = A_MN ? make_mnmajor_sw128_desc(sa) : make_kmajor_sw128_desc(sa);
+                    const uint64_t db = B_MN ? make_mnmajor_sw128_desc(sb) : make_kmajor_sw128_desc(sb);
+                    // UMMA K = 8 tf32: K-major advances 32 bytes inside the swizzle row, MN-major one 8-row group
+                    constexpr uint64_t stepA = A_MN ? (1024 >> 4) : (32 >> 4), stepB = B_MN ? (1024 >> 4) : (32 >> 4);
 #pragma unroll
-                    for (int k = 0; k < kBK / 8; ++k)  // UMMA K = 8 tf32 = 32 bytes: advance the start address
-                        umma_tf32(tmem_c, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < kBK / 8; ++k)
+                        umma_tf32(tmem_c, da + (uint64_t)k * stepA, db + (uint64_t)k * stepB, idesc, (kb | k) ? 1u : 0u);
                     umma_commit(&empty[stage]);
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -268,16 +296,21 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D fp32 tensor map over a K-major operand: rows x K, row pitch `pitch` elements; box = box_rows x 32.
-dn_status make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t K, int64_t pitch, int box_rows) {
+// 2-D fp32 tensor map: `inner` contiguous elements per line, `outer` lines `pitch` elements apart;
+// box = box_outer lines x 32 elements (128 bytes, one swizzle row).
+// K-major operand: inner = K, outer = rows (M or N), box_outer = tile rows.
+// MN-major operand: inner = rows (M or N), outer = K, box_outer = 32 k-rows.
+dn_status make_map(CUtensorMap *map, const float *base, int64_t outer, int64_t inner, int64_t pitch, int box_outer,
+                   bool mn_major = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(DN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(DN_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
     return DN_OK;
@@ -289,8 +322,11 @@ struct Operand2D {
     int64_t rows, K, rs, ks;
 };
 
-bool tma_ready(const Operand2D &o) {
+bool tma_ready(const Operand2D &o) {  // K-major in place
     return o.ks == 1 && o.rs >= o.K && (o.rs % 4) == 0 && (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0;
+}
+bool tma_ready_mn(const Operand2D &o) {  // MN-major in place: the row index is the contiguous one
+    return o.rs == 1 && o.ks >= o.rows && (o.ks % 4) == 0 && (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0;
 }
 
 // Repack into a fresh K-major buffer with a 16-byte aligned pitch (stream-ordered scratch).
@@ -316,18 +352,25 @@ dn_status repack_kmajor(Operand2D &o, void **scratch) {
     return DN_OK;
 }
 
-template <int BN>
+template <int BN, bool A_MN, bool B_MN>
 dn_status launch_tf32(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p) {
     using Cfg = GemmCfg<BN>;
     static bool configured = false;
     if (!configured) {
-        DN_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        DN_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes));
         configured = true;
     }
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    DN_LAUNCH((gemm_tf32_kernel<BN>), grid, kGemmThreads, Cfg::kSmemBytes, ma, mb, p);
+    DN_LAUNCH((gemm_tf32_kernel<BN, A_MN, B_MN>), grid, kGemmThreads, Cfg::kSmemBytes, ma, mb, p);
     return launch_status("tcgen05 GEMM kernel");
+}
+
+template <int BN>
+dn_status launch_tf32_major(bool a_mn, bool b_mn, const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p) {
+    if (a_mn) return b_mn ? launch_tf32<BN, true, true>(ma, mb, p) : launch_tf32<BN, true, false>(ma, mb, p);
+    return b_mn ? launch_tf32<BN, false, true>(ma, mb, p) : launch_tf32<BN, false, false>(ma, mb, p);
 }
 
 // C[M,N] (strides cm, cn) = A[M,K] (am, ak) · B[K,N] (bk, bn), fp32.
@@ -345,8 +388,10 @@ dn_status gemm_f32(float *c, int64_t cm, int64_t cn, const float *a, int64_t am,
     Operand2D A{a, M, K, am, ak}, B{b, N, K, bn, bk};  // B viewed as [N, K]
     void *sa = nullptr, *sb = nullptr;
     dn_status st = DN_OK;
-    if (!tma_ready(A)) st = repack_kmajor(A, &sa);
-    if (st == DN_OK && !tma_ready(B)) st = repack_kmajor(B, &sb);
+    // operand classes: K-major in place, MN-major in place, or repacked K-major
+    const bool a_mn = !tma_ready(A) && tma_ready_mn(A), b_mn = !tma_ready(B) && tma_ready_mn(B);
+    if (!a_mn && !tma_ready(A)) st = repack_kmajor(A, &sa);
+    if (st == DN_OK && !b_mn && !tma_ready(B)) st = repack_kmajor(B, &sb);
     CUtensorMap ma, mb;
     GemmParams p;
     p.c = c; p.ldc_m = cm; p.ldc_n = cn;
@@ -354,12 +399,12 @@ dn_status gemm_f32(float *c, int64_t cm, int64_t cn, const float *a, int64_t am,
     const int BN = N <= 32 ? 32 : (N <= 128 ? 128 : 256);
     p.tiles_m = (int32_t)((M + kBM - 1) / kBM);
     p.tiles_n = (int32_t)((N + BN - 1) / BN);
-    if (st == DN_OK) st = make_map(&ma, A.ptr, A.rows, K, A.rs, kBM);
-    if (st == DN_OK) st = make_map(&mb, B.ptr, B.rows, K, B.rs, BN);
+    if (st == DN_OK) st = a_mn ? make_map(&ma, A.ptr, K, A.rows, A.ks, kBK, true) : make_map(&ma, A.ptr, A.rows, K, A.rs, kBM);
+    if (st == DN_OK) st = b_mn ? make_map(&mb, B.ptr, K, B.rows, B.ks, kBK, true) : make_map(&mb, B.ptr, B.rows, K, B.rs, BN);
     if (st == DN_OK) {
-        if (BN == 32) st = launch_tf32<32>(ma, mb, p);
-        else if (BN == 128) st = launch_tf32<128>(ma, mb, p);
-        else st = launch_tf32<256>(ma, mb, p);
+        if (BN == 32) st = launch_tf32_major<32>(a_mn, b_mn, ma, mb, p);
+        else if (BN == 128) st = launch_tf32_major<128>(a_mn, b_mn, ma, mb, p);
+        else st = launch_tf32_major<256>(a_mn, b_mn, ma, mb, p);
     }
     scratch_free(sa);
     scratch_free(sb);
