@@ -130,7 +130,8 @@ struct GemmCfg {
     static constexpr int kStageBytes = (kBM + BN) * kBK * 4;
     static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages, power of two >= 32
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kEpiBytes = 4 * 32 * 33 * 4;  // per-epilogue-warp transpose staging
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiBytes;
 };
 
 // A_MN / B_MN: the operand is MN-major (its M resp. N axis is the contiguous one) and is consumed in place.
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_kernel(const __grid
     uint64_t *full = bars, *empty = bars + Cfg::kStages;
     uint64_t *tmem_full = bars + 2 * Cfg::kStages, *tmem_empty = tmem_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *epi = reinterpret_cast<float *>(smem + Cfg::kStages * Cfg::kStageBytes + 256);  // 4 warps x 32 x 33 floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = p.tiles_m * p.tiles_n;
@@ -251,18 +253,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_kernel(const __grid
                 if (col >= p.N) break;  // warp-uniform
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + (uint32_t)c0, r);
-                if (row < p.M) {
-                    float *crow = p.c + (int64_t)row * p.ldc_m + (int64_t)col * p.ldc_n;
-                    if (vec_ok && col + 32 <= p.N) {
+                if (vec_ok && col + 32 <= p.N) {
+                    // Row-major C: transpose the warp's 32x32 block through shared memory so that every store
+                    // instruction writes 4 rows x 128 contiguous bytes (lane -> row lane/8, columns 4*(lane%8)..+3)
+                    // instead of 32 rows x 16 bytes.
+                    float *blk = epi + (warp - 2) * (32 * 33);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4 *>(crow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                    } else {
+                    for (int j = 0; j < 32; ++j) blk[lane * 33 + j] = __uint_as_float(r[j]);
+                    __syncwarp();
+                    const int cg = (lane & 7) * 4;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col + j < p.N) crow[(int64_t)j * p.ldc_n] = __uint_as_float(r[j]);
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + (lane >> 3);
+                        const int grow = m_blk * kBM + quarter * 32 + rr;
+                        if (grow < p.M) {
+                            const float *sp = blk + rr * 33 + cg;
+                            *reinterpret_cast<float4 *>(p.c + (int64_t)grow * p.ldc_m + col + cg) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                        }
                     }
+                    __syncwarp();
+                } else if (row < p.M) {
+                    float *crow = p.c + (int64_t)row * p.ldc_m + (int64_t)col * p.ldc_n;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col + j < p.N) crow[(int64_t)j * p.ldc_n] = __uint_as_float(r[j]);
                 }
             }
             tcgen05_fence_before();
