@@ -105,31 +105,22 @@ __global__ void __launch_bounds__(kIdxThreads) gather_kernel(const __grid_consta
     }
 }
 
-// atomic add for every numeric element type (Scatter sums duplicates; GatherScatter.cuh:89 uses atomicAdd, which
-// has no int64 / 16-bit / 8-bit overloads — those go through unsigned wrap-around or a CAS on the enclosing word).
+// atomic add for the element types that have a native red/atom: f32, f64, i32, u32, u64; int64 goes through the
+// unsigned 64-bit add (two's complement wrap-around is the same operation). GatherScatter.cuh:89 relies on
+// atomicAdd overloads and therefore cannot instantiate int64 at all. 8- and 16-bit targets never reach this
+// function: dn_scatter accumulates them in a 32-bit scratch tensor and narrows afterwards (no sub-word CAS, no
+// access outside the target's own bytes).
 template <class T> __device__ __forceinline__ void atomic_add_any(T *addr, T v) {
-    if constexpr (std::is_same<T, float>::value || std::is_same<T, double>::value ||
-                  std::is_same<T, int32_t>::value || std::is_same<T, uint32_t>::value) {
-        atomicAdd(addr, v);
-    } else if constexpr (sizeof(T) == 8) {
+    if constexpr (sizeof(T) == 8 && std::is_integral<T>::value) {
         atomicAdd(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)v);
     } else {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(addr);
-        unsigned *word = reinterpret_cast<unsigned *>(a & ~(uintptr_t)3);
-        const unsigned shift = (unsigned)(a & 3) * 8;
-        const unsigned mask = (sizeof(T) == 1 ? 0xffu : 0xffffu) << shift;
-        unsigned old = *word, assumed;
-        do {
-            assumed = old;
-            const unsigned cur = (assumed & mask) >> shift;
-            const unsigned sum = (cur + (unsigned)(typename std::make_unsigned<T>::type)v) << shift;
-            old = atomicCAS(word, assumed, (assumed & ~mask) | (sum & mask));
-        } while (old != assumed);
+        atomicAdd(addr, v);
     }
 }
 
-template <class T>
+template <class TS, class TA>
 __global__ void __launch_bounds__(kIdxThreads) scatter_kernel(const __grid_constant__ GSParams p) {
+    using T = TA;
     constexpr int U = 4;
     for (uint64_t base = (uint64_t)blockIdx.x * (kIdxThreads * U); base < p.n; base += (uint64_t)gridDim.x * (kIdxThreads * U)) {
         int64_t so[U], to[U];
@@ -141,7 +132,7 @@ __global__ void __launch_bounds__(kIdxThreads) scatter_kernel(const __grid_const
             state[j] = 0;
             if (f < p.n) {
                 state[j] = gs_addresses(p, (uint32_t)f, so[j], to[j]) ? 1 : 2;
-                v[j] = *reinterpret_cast<const T *>(p.it_ptr + so[j]);
+                v[j] = (TA)*reinterpret_cast<const TS *>(p.it_ptr + so[j]);
             }
         }
 #pragma unroll
@@ -618,29 +609,50 @@ dn_status dn_scatter(const dn_tensor *t, const dn_tensor *const *idxs, int32_t n
     dn_status st = validate_gs(a, t, idxs, nidxs, "Scatter");
     if (st != DN_OK) return st;
     if (t->dtype == DN_BOOL) return set_error(DN_ERR_UNSUPPORTED, "Scatter is not defined for type bool (no addition)");
+    const int esize = dtype_size(t->dtype);
+    const int64_t nt = num_elements(t);
+    // 8/16-bit element types have no native atomic add: accumulate in a dense int32 scratch tensor of the target's
+    // shape (sums agree modulo 2^8 / 2^16, i.e. the host's wrapping arithmetic) and narrow into the target.
+    dn_tensor acc = *t;
+    void *scratch = nullptr;
+    if (esize < 4) {
+        st = scratch_alloc((size_t)(nt > 0 ? nt : 1) * 4, &scratch);
+        if (st != DN_OK) return st;
+        acc.base = scratch;
+        acc.offset = 0;
+        acc.dtype = DN_I32;
+        int64_t stride = 1;
+        for (int d = t->ndims - 1; d >= 0; --d) {
+            acc.stride[d] = stride;
+            stride *= t->shape[d];
+        }
+    }
     // zero-fill (CudaBackend.fs:379), then accumulate
     uint64_t zero = 0;
-    st = dn_fill_const(t, &zero);
-    if (st != DN_OK) return st;
-    if (num_elements(a) == 0) return DN_OK;
-    GSParams p;
-    st = gs_fill(p, a, t, idxs, "Scatter");
-    if (st != DN_OK) return st;
-    const int grid = ew_grid_for(p.n, kIdxThreads * 4);
-    switch (t->dtype) {
-    case DN_F32: DN_LAUNCH((scatter_kernel<float>), grid, kIdxThreads, 0, p); break;
-    case DN_F64: DN_LAUNCH((scatter_kernel<double>), grid, kIdxThreads, 0, p); break;
-    case DN_I8: DN_LAUNCH((scatter_kernel<int8_t>), grid, kIdxThreads, 0, p); break;
-    case DN_U8: DN_LAUNCH((scatter_kernel<uint8_t>), grid, kIdxThreads, 0, p); break;
-    case DN_I16: DN_LAUNCH((scatter_kernel<int16_t>), grid, kIdxThreads, 0, p); break;
-    case DN_U16: DN_LAUNCH((scatter_kernel<uint16_t>), grid, kIdxThreads, 0, p); break;
-    case DN_I32: DN_LAUNCH((scatter_kernel<int32_t>), grid, kIdxThreads, 0, p); break;
-    case DN_U32: DN_LAUNCH((scatter_kernel<uint32_t>), grid, kIdxThreads, 0, p); break;
-    case DN_I64: DN_LAUNCH((scatter_kernel<int64_t>), grid, kIdxThreads, 0, p); break;
-    case DN_U64: DN_LAUNCH((scatter_kernel<uint64_t>), grid, kIdxThreads, 0, p); break;
-    default: return set_error(DN_ERR_INVALID_ARG, "bad dtype");
+    st = dn_fill_const(&acc, &zero);
+    if (st == DN_OK && num_elements(a) > 0) {
+        GSParams p;
+        st = gs_fill(p, a, &acc, idxs, "Scatter");
+        if (st == DN_OK) {
+            const int grid = ew_grid_for(p.n, kIdxThreads * 4);
+            switch (t->dtype) {
+            case DN_F32: DN_LAUNCH((scatter_kernel<float, float>), grid, kIdxThreads, 0, p); break;
+            case DN_F64: DN_LAUNCH((scatter_kernel<double, double>), grid, kIdxThreads, 0, p); break;
+            case DN_I8: DN_LAUNCH((scatter_kernel<int8_t, int32_t>), grid, kIdxThreads, 0, p); break;
+            case DN_U8: DN_LAUNCH((scatter_kernel<uint8_t, int32_t>), grid, kIdxThreads, 0, p); break;
+            case DN_I16: DN_LAUNCH((scatter_kernel<int16_t, int32_t>), grid, kIdxThreads, 0, p); break;
+            case DN_U16: DN_LAUNCH((scatter_kernel<uint16_t, int32_t>), grid, kIdxThreads, 0, p); break;
+            case DN_I32: DN_LAUNCH((scatter_kernel<int32_t, int32_t>), grid, kIdxThreads, 0, p); break;
+            case DN_U32: DN_LAUNCH((scatter_kernel<uint32_t, uint32_t>), grid, kIdxThreads, 0, p); break;
+            case DN_I64: DN_LAUNCH((scatter_kernel<int64_t, int64_t>), grid, kIdxThreads, 0, p); break;
+            case DN_U64: DN_LAUNCH((scatter_kernel<uint64_t, uint64_t>), grid, kIdxThreads, 0, p); break;
+            default: st = set_error(DN_ERR_INVALID_ARG, "bad dtype"); break;
+            }
+            if (st == DN_OK) st = launch_status("scatter kernel");
+        }
     }
-    st = launch_status("scatter kernel");
+    if (st == DN_OK && esize < 4) st = dn_convert(t, &acc);  // unchecked narrowing = wrap-around
+    scratch_free(scratch);
     if (st != DN_OK) return st;
     return check_index_error("Scatter");
 }
