@@ -6,7 +6,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 HOSTCXX   := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin $(HOSTCXX) --expt-relaxed-constexpr \
-             -Xcudafe --diag_suppress=177 -Xptxas -warn-spills
+             -Xcudafe --diag_suppress=177 -Xptxas -warn-spills -Xfatbin=-compress-all
 SRC       := deepnet_b200/csrc
 OBJ       := build/obj
 LIB       := deepnet_b200/lib/libdeepnet_b200.so

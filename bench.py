@@ -406,9 +406,18 @@ def main():
     peak, peak_src = load_peaks()
     # dominant kernel = the call with the largest share of the step
     dom = max(per_call, key=lambda x: x[2])
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the same calls
+    # (profiles/r01_*.raw.csv); None for calls that have not been captured
+    ncu_traffic = {
+        "single add contiguous": 2.155864e9 + 1.036331e9,      # profiles/r01_ew_add_contig.raw.csv
+        "single add a.T + b": 2.147507e9 + 1.039083e9,         # profiles/r01_ew_xpose_addT.raw.csv
+        "single add a[1:,1:] + b[1:,1:]": 2.152425e9 + 1.035520e9,  # profiles/r01_ew_sliced.raw.csv
+        "double add a.T + b": 4.295036e9 + 2.110988e9,         # profiles/r01_ew_xpose_f64_addT.raw.csv
+    }
     roofline = {
         "bound": "hbm", "kernel": dom[0], "achieved": dom[1] / dom[2] / 1e6, "peak": peak, "unit": "GB/s",
-        "frac": dom[1] / dom[2] / 1e6 / peak, "traffic": None, "peak_source": peak_src,
+        "frac": dom[1] / dom[2] / 1e6 / peak, "traffic": ncu_traffic.get(dom[0]) if side == SIDE else None,
+        "algorithmic_bytes": dom[1], "peak_source": peak_src,
         "share_of_step": dom[2] / sum(x[2] for x in per_call),
         "per_call_gbs": {n: round(nb / ms / 1e6, 1) for n, nb, ms in per_call},
         "step_frac_of_peak": (step_bytes / (ms_per_step * 1e-3) / 1e9) / peak if world == 1 else value / world / peak,
