@@ -356,10 +356,21 @@ struct CoordSink {  // TrueIndices: t[rank, d] = coordinate d of the element (de
     int64_t ts0, ts1;  // bytes
     int64_t cap;       // rows available in t
     int32_t nd;
-    uint32_t shape[DN_MAX_DIMS];  // innermost-first (same as the BoolView)
+    int32_t dense;     // t is row-major contiguous and 16-byte aligned: rows of 1 or 2 coordinates are one store
+    uint32_t shape[DN_MAX_DIMS];  // innermost-first (the ORIGINAL dims of the view)
     FastDiv div[DN_MAX_DIMS];
     __device__ __forceinline__ void operator()(int64_t rank, uint32_t f) const {
         if (rank >= cap) return;
+        if (dense && nd == 2) {  // the common case (matrix mask): one division, one 128-bit store per row
+            const uint32_t q = div[0].div(f);
+            const longlong2 row = make_longlong2((long long)q, (long long)(f - q * shape[0]));
+            *reinterpret_cast<longlong2 *>(t + rank * 16) = row;
+            return;
+        }
+        if (dense && nd == 1) {
+            *reinterpret_cast<int64_t *>(t + rank * 8) = (int64_t)f;
+            return;
+        }
         uint32_t rem = f;
 #pragma unroll
         for (int k = 0; k < DN_MAX_DIMS; ++k) {
@@ -461,6 +472,32 @@ dn_status make_bool_view(BoolView &v, const dn_tensor *a, const char *what) {
         v.stride[0] = 0;
     }
     return DN_OK;
+}
+
+// Merges adjacent dims that are contiguous in row-major order (and drops size-1 dims); the logical walk order is
+// unchanged, the index math gets shorter and contiguous masks become 1-D (one 128-bit load per 16 positions).
+void merge_bool_view(BoolView &v) {
+    uint32_t shape[DN_MAX_DIMS];
+    int64_t stride[DN_MAX_DIMS];
+    int m = 0;
+    for (int k = 0; k < v.nd; ++k) {  // innermost-first
+        if (v.shape[k] == 1) continue;
+        if (m > 0 && v.stride[k] == stride[m - 1] * (int64_t)shape[m - 1] &&
+            (uint64_t)shape[m - 1] * v.shape[k] < (1ull << 31)) {
+            shape[m - 1] *= v.shape[k];
+            continue;
+        }
+        shape[m] = v.shape[k];
+        stride[m] = v.stride[k];
+        ++m;
+    }
+    if (m == 0) { shape[0] = 1; stride[0] = 0; m = 1; }
+    v.nd = m;
+    for (int k = 0; k < DN_MAX_DIMS; ++k) {
+        v.shape[k] = k < m ? shape[k] : 1;
+        v.stride[k] = k < m ? stride[k] : 0;
+        v.div[k].init(v.shape[k]);
+    }
 }
 
 int tiles_grid(uint32_t ntiles) {
@@ -664,6 +701,7 @@ dn_status dn_count_true(const dn_tensor *a, int64_t *count) {
     dn_status st = make_bool_view(m, a, "countTrue");
     if (st != DN_OK) return st;
     if (m.n == 0) return DN_OK;
+    merge_bool_view(m);
     void *scratch = nullptr;
     st = scratch_alloc(sizeof(unsigned long long), &scratch);
     if (st != DN_OK) return st;
@@ -693,10 +731,12 @@ dn_status dn_true_indices(const dn_tensor *t, const dn_tensor *a) {
     sink.ts1 = t->stride[1] * 8;
     sink.cap = t->shape[0];
     sink.nd = m.nd;
-    for (int k = 0; k < DN_MAX_DIMS; ++k) {
+    sink.dense = (t->stride[1] == 1 && t->stride[0] == t->shape[1] && (reinterpret_cast<uintptr_t>(sink.t) & 15) == 0) ? 1 : 0;
+    for (int k = 0; k < DN_MAX_DIMS; ++k) {  // coordinates are reported in the ORIGINAL dims
         sink.shape[k] = m.shape[k];
         sink.div[k] = m.div[k];
     }
+    merge_bool_view(m);  // reading may use the merged view
     return run_compaction(m, sink);
 }
 
