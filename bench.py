@@ -424,13 +424,24 @@ def main():
     }
 
     # ---- e2e arm: pinned host buffers -> H2D -> same calls -> D2H of one result per dtype ---------------------
+    # Pinned host buffers (8 GiB per rank at the default size): float32 and int32 share one pair of input buffers
+    # (the int32 cases upload the same bytes), float64 has its own pair, one download buffer is shared.
     e2e_side = side
-    pinned, e2e_sets = [], []
+    pinned = []
     h2d = d2h = 0
+    out_buf = torch.empty(e2e_side * e2e_side * 8, dtype=torch.uint8).pin_memory()
+    shared32 = None
     for dt, npdt, has_sin in dtype_list():
-        an, bn, rn, cn = host_inputs(rng, e2e_side, npdt)
-        hp = [torch.from_numpy(x).pin_memory() for x in (an, bn, rn, cn)]
-        out = torch.empty((e2e_side, e2e_side), dtype=torch_dt[dt]).pin_memory()
+        isz = dtypes.itemsize(dt)
+        if isz == 4 and shared32 is not None:
+            hp = [x.view(torch_dt[dt]) for x in shared32]
+        else:
+            an, bn, _, _ = host_inputs(rng, e2e_side, npdt)
+            hp = [torch.from_numpy(x).pin_memory() for x in (an, bn)]
+            del an, bn
+            if isz == 4:
+                shared32 = hp
+        out = out_buf[: e2e_side * e2e_side * isz].view(torch_dt[dt]).view(e2e_side, e2e_side)
         pinned.append((hp, out))
         h2d += sum(x.numel() * x.element_size() for x in hp)
         d2h += out.numel() * out.element_size()
