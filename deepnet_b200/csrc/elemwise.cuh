@@ -466,7 +466,7 @@ int ew_grid_for(int64_t work_items, int items_per_cta);
 int ew_xpose_mode(const EwPlan &plan, int k, int dS, int m);
 
 template <int NOPS>
-void ew_fill_params(EwParams<NOPS> &p, const EwPlan &plan, int vec, int64_t outer_begin, int64_t outer_count) {
+void ew_fill_params(EwParams<NOPS> &p, const EwPlan &plan, int vec) {
     const int nd = plan.ndims;
     p.ndims = nd;
     p.splat_mask = 0;
@@ -474,7 +474,6 @@ void ew_fill_params(EwParams<NOPS> &p, const EwPlan &plan, int vec, int64_t oute
     for (int d = 0; d < DN_MAX_DIMS; ++d) {
         int64_t s = d < nd ? plan.shape[d] : 1;
         if (d == 0) s /= vec;
-        if (d == nd - 1) s = outer_count;  // the chunk runs along the outermost dim (work items when nd == 1)
         p.shape[d] = (uint32_t)s;
         p.div[d].init((uint32_t)(s > 0 ? s : 1));
         if (d < nd) n *= (uint64_t)s;
@@ -488,9 +487,7 @@ void ew_fill_params(EwParams<NOPS> &p, const EwPlan &plan, int vec, int64_t oute
             p.stride[k][d] = st;
         }
         if (o.stride[0] == 0) p.splat_mask |= 1u << k;
-        const int od = nd - 1;
-        const int64_t step = o.stride[od] * o.esize * ((nd == 1) ? vec : 1);
-        p.ptr[k] = o.ptr + outer_begin * step;
+        p.ptr[k] = o.ptr;
     }
 }
 
@@ -500,34 +497,43 @@ void ew_launch_one(const EwParams<F::NSRC + 1> &p, const F &f) {
     DN_LAUNCH((ew_kernel<F, VEC, U, ND>), grid, kEwThreads, 0, p, f);
 }
 
+// Launches the strided kernel over `plan` (dim 0 holds a multiple of VEC elements). One launch covers at most
+// 2^30 work items (32-bit index math); larger plans are halved along their outermost non-trivial dim, recursively.
 template <class F, int VEC>
 dn_status ew_launch_strided(const EwPlan &plan, const F &f, int64_t n_inner0_elems) {
     constexpr int NOPS = F::NSRC + 1;
     // U: independent work items per thread; 64-128 bytes of loads per source in flight per thread
     constexpr int U = VEC == 1 ? (F::MaxSize >= 8 ? 4 : 8) : ((VEC * F::MaxSize >= 64) ? 1 : ((VEC * F::MaxSize >= 32) ? 2 : 4));
-    const int nd = plan.ndims;
-    int64_t inner = 1;  // work items of all dims but the outermost
-    for (int d = 0; d < nd - 1; ++d) inner *= (d == 0 ? n_inner0_elems / VEC : plan.shape[d]);
-    const int64_t outer_total = (nd == 1) ? n_inner0_elems / VEC : plan.shape[nd - 1];
-    const int64_t max_items = (int64_t)1 << 30;
-    const int64_t chunk = inner > 0 ? max_items / inner : max_items;
-    if (chunk < 1) return set_error(DN_ERR_UNSUPPORTED, "element-wise: inner extent exceeds 2^30 work items");
     EwPlan local = plan;
     local.shape[0] = n_inner0_elems;
-    for (int64_t begin = 0; begin < outer_total; begin += chunk) {
-        const int64_t count = (outer_total - begin < chunk) ? outer_total - begin : chunk;
-        EwParams<NOPS> p;
-        ew_fill_params<NOPS>(p, local, VEC, begin, count);
-        if (p.n == 0) continue;
-        if constexpr (VEC == 1) {
-            // scalar path: the rank is a compile-time constant for the common cases
-            if (nd == 1) ew_launch_one<F, 1, U, 1>(p, f);
-            else if (nd == 2) ew_launch_one<F, 1, U, 2>(p, f);
-            else if (nd == 3) ew_launch_one<F, 1, U, 3>(p, f);
-            else ew_launch_one<F, 1, U, 0>(p, f);
-        } else {
-            ew_launch_one<F, VEC, U, 0>(p, f);
-        }
+    const int nd = local.ndims;
+    int64_t items = local.shape[0] / VEC;
+    for (int d = 1; d < nd; ++d) items *= local.shape[d];
+    if (items == 0) return DN_OK;
+    if (items > ((int64_t)1 << 30)) {
+        int d = nd - 1;
+        while (d > 0 && local.shape[d] == 1) --d;
+        const int64_t unit = d == 0 ? VEC : 1;
+        const int64_t half = (local.shape[d] / unit / 2) * unit;
+        if (half <= 0) return set_error(DN_ERR_UNSUPPORTED, "element-wise: cannot split a plan of %lld work items", (long long)items);
+        EwPlan lo = local, hi = local;
+        lo.shape[d] = half;
+        hi.shape[d] = local.shape[d] - half;
+        for (int k = 0; k < NOPS; ++k) hi.op[k].ptr += half * hi.op[k].stride[d] * hi.op[k].esize;
+        dn_status st = ew_launch_strided<F, VEC>(lo, f, lo.shape[0]);
+        if (st != DN_OK) return st;
+        return ew_launch_strided<F, VEC>(hi, f, hi.shape[0]);
+    }
+    EwParams<NOPS> p;
+    ew_fill_params<NOPS>(p, local, VEC);
+    if constexpr (VEC == 1) {
+        // scalar path: the rank is a compile-time constant for the common cases
+        if (nd == 1) ew_launch_one<F, 1, U, 1>(p, f);
+        else if (nd == 2) ew_launch_one<F, 1, U, 2>(p, f);
+        else if (nd == 3) ew_launch_one<F, 1, U, 3>(p, f);
+        else ew_launch_one<F, 1, U, 0>(p, f);
+    } else {
+        ew_launch_one<F, VEC, U, 0>(p, f);
     }
     return launch_status("element-wise kernel");
 }

@@ -24,14 +24,14 @@ dn_status red_make_plan(RedPlan &plan, const dn_tensor *t, const dn_tensor *a, c
     Dim dims[DN_MAX_DIMS];
     int n = 0;
     int64_t rows = 1;
+    for (int d = nd - 2; d >= 0; --d) rows *= a->shape[d];
+    plan.nrows = rows;
+    if (rows == 0) return DN_OK;  // (row-major strides in front of a zero-sized dim are 0: nothing to validate)
     for (int d = nd - 2; d >= 0; --d) {  // innermost-first
-        rows *= a->shape[d];
         if (a->shape[d] == 1) continue;
         if (t->stride[d] == 0) return set_error(DN_ERR_INVALID_ARG, "%s: the target must not be a broadcast view", what);
         dims[n++] = Dim{a->shape[d], a->stride[d], t->stride[d]};
     }
-    plan.nrows = rows;
-    if (rows == 0) return DN_OK;
     std::stable_sort(dims, dims + n, [](const Dim &x, const Dim &y) {
         const int64_t ax = x.ss < 0 ? -x.ss : x.ss, ay = y.ss < 0 ? -y.ss : y.ss;
         return ax < ay;
