@@ -510,11 +510,38 @@ dn_status mm_one(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b, int
 // ---------------------------------------------------------------------------------------------------------------
 // VecVecDot / MatVecDot: HBM-bound, one pass over the operands
 // ---------------------------------------------------------------------------------------------------------------
-template <class T>
+// VecVecDot partial sums. VEC > 1: both vectors contiguous and 16-byte aligned -> 128-bit loads, 4 per operand in flight.
+template <class T, int VEC>
 __global__ void __launch_bounds__(256) dot_partial_kernel(const T *a, int64_t as, const T *b, int64_t bs, int64_t n, T *partials) {
     T acc = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        acc += a[i * as] * b[i * bs];
+    if constexpr (VEC > 1) {
+        const int64_t nv = n / VEC;
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < nv; i += 4 * stride) {
+            Pack<T, VEC> x[4], y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                x[u] = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(a + (i + u * stride) * VEC));
+                y[u] = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(b + (i + u * stride) * VEC));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc += x[u].v[j] * y[u].v[j];
+        }
+        for (; i < nv; i += stride) {
+            const Pack<T, VEC> x = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(a + i * VEC));
+            const Pack<T, VEC> y = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(b + i * VEC));
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc += x.v[j] * y.v[j];
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            for (int64_t k = nv * VEC; k < n; ++k) acc += a[k] * b[k];
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+            acc += a[i * as] * b[i * bs];
+    }
     __shared__ T sm[8];
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
@@ -535,26 +562,134 @@ __global__ void dot_final_kernel(const T *partials, int n, T *out) {
     if (threadIdx.x == 0) *out = acc;
 }
 
-// y[m] = sum_k A[m,k] x[k]; warp per row when k is the contiguous axis, thread per row otherwise.
+// y[m] = sum_k A[m,k] x[k].
+// mode 2: k contiguous in A and x, 16-byte aligned rows -> a warp per row with 128-bit loads (x stays in L1/L2);
+// mode 1: k is A's faster axis but not vectorisable -> warp per row, scalar.
+// (m the faster axis, i.e. a transposed view: matvec_t_kernel below.)
 template <class T>
 __global__ void __launch_bounds__(256) matvec_kernel(T *y, int64_t ys, const T *a, int64_t am, int64_t ak, const T *x, int64_t xs,
-                                                    int64_t M, int64_t K, int warp_per_row) {
-    if (warp_per_row) {
+                                                    int64_t M, int64_t K, int mode) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    {
         const int lane = threadIdx.x & 31;
         for (int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); m < M; m += (int64_t)gridDim.x * 8) {
             T acc = 0;
-            for (int64_t k = lane; k < K; k += 32) acc += a[m * am + k * ak] * x[k * xs];
+            const T *row = a + m * am;
+            if (mode == 2) {
+                const int64_t kv = K / VEC;
+                int64_t k = lane;
+                for (; k + 96 < kv; k += 128) {
+                    Pack<T, VEC> av[4], xv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        av[u] = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(row + (k + 32 * u) * VEC));
+                        xv[u] = *reinterpret_cast<const Pack<T, VEC> *>(x + (k + 32 * u) * VEC);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) acc += av[u].v[j] * xv[u].v[j];
+                }
+                for (; k < kv; k += 32) {
+                    const Pack<T, VEC> av = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(row + k * VEC));
+                    const Pack<T, VEC> xv = *reinterpret_cast<const Pack<T, VEC> *>(x + k * VEC);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc += av.v[j] * xv.v[j];
+                }
+                for (int64_t kk = kv * VEC + lane; kk < K; kk += 32) acc += row[kk] * x[kk];
+            } else {
+                for (int64_t k = lane; k < K; k += 32) acc += row[k * ak] * x[k * xs];
+            }
 #pragma unroll
             for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
             if (lane == 0) y[m * ys] = acc;
         }
-    } else {
-        for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
-            T acc = 0;
-            for (int64_t k = 0; k < K; ++k) acc += a[m * am + k * ak] * x[k * xs];
-            y[m * ys] = acc;
-        }
     }
+}
+
+// MatVecDot for a matrix whose faster axis is m (a transposed view): a thread owns VEC consecutive rows and one
+// K-slice; slices are combined in slice order by matvec_t_final_kernel (deterministic, no atomics).
+template <class T, int VEC>
+__global__ void __launch_bounds__(256) matvec_t_kernel(T *out, int64_t out_ms, int64_t out_ss, const T *a, int64_t am, int64_t ak,
+                                                      const T *x, int64_t xs, int64_t M, int64_t K, int64_t kchunk) {
+    const int64_t mv = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (mv >= M) return;
+    const int64_t k0 = (int64_t)blockIdx.y * kchunk;
+    const int64_t k1 = k0 + kchunk < K ? k0 + kchunk : K;
+    T acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0;
+    const T *col = a + mv * am;
+    int64_t k = k0;
+    for (; k + 4 <= k1; k += 4) {
+        Pack<T, VEC> av[4];
+        T xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if constexpr (VEC > 1) av[u] = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(col + (k + u) * ak));
+            else av[u].v[0] = col[(k + u) * ak];
+            xv[u] = x[(k + u) * xs];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] += av[u].v[j] * xv[u];
+    }
+    for (; k < k1; ++k) {
+        const T xk = x[k * xs];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] += col[k * ak + j * am] * xk;
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[(mv + j) * out_ms + (int64_t)blockIdx.y * out_ss] = acc[j];
+}
+template <class T>
+__global__ void matvec_t_final_kernel(T *y, int64_t ys, const T *partials, int64_t M, int slices) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    T acc = 0;
+    for (int s = 0; s < slices; ++s) acc += partials[(int64_t)s * M + m];
+    y[m * ys] = acc;
+}
+
+template <class T>
+dn_status matvec_t_run(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const int64_t M = a->shape[0], K = a->shape[1];
+    const bool vec = a->stride[0] == 1 && M % V == 0 && (a->stride[1] * (int64_t)sizeof(T)) % 16 == 0 &&
+                     (reinterpret_cast<uintptr_t>(data_ptr(a)) & 15) == 0;
+    const int64_t threads = vec ? M / V : M;
+    const int64_t gx = (threads + 255) / 256;
+    // enough K-slices to fill the machine, each at least 64 deep
+    int64_t slices = ((int64_t)sm_count() * 8 + gx - 1) / gx;
+    if (slices > (K + 63) / 64) slices = (K + 63) / 64;
+    if (slices < 1) slices = 1;
+    if (slices > 65535) slices = 65535;
+    const int64_t kchunk = (K + slices - 1) / slices;
+    slices = K > 0 ? (K + kchunk - 1) / kchunk : 1;
+    T *dst = (T *)data_ptr(t);
+    int64_t out_ms = t->stride[0], out_ss = 0;
+    void *scratch = nullptr;
+    if (slices > 1) {
+        dn_status st = scratch_alloc((size_t)slices * M * sizeof(T), &scratch);
+        if (st != DN_OK) return st;
+        dst = (T *)scratch;
+        out_ms = 1;
+        out_ss = M;
+    }
+    const dim3 grid((unsigned)gx, (unsigned)slices);
+    if (vec)
+        DN_LAUNCH((matvec_t_kernel<T, V>), grid, 256, 0, dst, out_ms, out_ss, (const T *)data_ptr(a), a->stride[0], a->stride[1],
+                  (const T *)data_ptr(b), b->stride[0], M, K, kchunk);
+    else
+        DN_LAUNCH((matvec_t_kernel<T, 1>), grid, 256, 0, dst, out_ms, out_ss, (const T *)data_ptr(a), a->stride[0], a->stride[1],
+                  (const T *)data_ptr(b), b->stride[0], M, K, kchunk);
+    if (slices > 1) {
+        DN_LAUNCH(matvec_t_final_kernel<T>, (unsigned)((M + 255) / 256), 256, 0, (T *)data_ptr(t), t->stride[0], (const T *)scratch, M,
+                  (int)slices);
+        scratch_free(scratch);
+    }
+    return launch_status("MatVecDot kernels");
 }
 
 }  // namespace
@@ -596,20 +731,31 @@ dn_status dn_vec_vec_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor
     if (t->dtype != a->dtype || t->dtype != b->dtype || (t->dtype != DN_F32 && t->dtype != DN_F64))
         return set_error(DN_ERR_UNSUPPORTED, "VecVecDot is only supported for single and double");
     const int64_t n = a->shape[0];
-    int grid = (int)((n + 2047) / 2048);
+    int grid = (int)((n + 8191) / 8192);
     const int cap = sm_count() * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     void *scratch = nullptr;
     dn_status st = scratch_alloc((size_t)grid * 8, &scratch);
     if (st != DN_OK) return st;
+    const int esz = dtype_size(t->dtype);
+    const bool vec = a->stride[0] == 1 && b->stride[0] == 1 && (reinterpret_cast<uintptr_t>(data_ptr(a)) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(data_ptr(b)) & 15) == 0 && n >= 16 / esz;
     if (t->dtype == DN_F32) {
-        DN_LAUNCH(dot_partial_kernel<float>, grid, 256, 0, (const float *)data_ptr(a), a->stride[0], (const float *)data_ptr(b),
-                  b->stride[0], n, (float *)scratch);
+        if (vec)
+            DN_LAUNCH((dot_partial_kernel<float, 4>), grid, 256, 0, (const float *)data_ptr(a), a->stride[0],
+                      (const float *)data_ptr(b), b->stride[0], n, (float *)scratch);
+        else
+            DN_LAUNCH((dot_partial_kernel<float, 1>), grid, 256, 0, (const float *)data_ptr(a), a->stride[0],
+                      (const float *)data_ptr(b), b->stride[0], n, (float *)scratch);
         DN_LAUNCH(dot_final_kernel<float>, 1, 32, 0, (const float *)scratch, grid, (float *)data_ptr(t));
     } else {
-        DN_LAUNCH(dot_partial_kernel<double>, grid, 256, 0, (const double *)data_ptr(a), a->stride[0], (const double *)data_ptr(b),
-                  b->stride[0], n, (double *)scratch);
+        if (vec)
+            DN_LAUNCH((dot_partial_kernel<double, 2>), grid, 256, 0, (const double *)data_ptr(a), a->stride[0],
+                      (const double *)data_ptr(b), b->stride[0], n, (double *)scratch);
+        else
+            DN_LAUNCH((dot_partial_kernel<double, 1>), grid, 256, 0, (const double *)data_ptr(a), a->stride[0],
+                      (const double *)data_ptr(b), b->stride[0], n, (double *)scratch);
         DN_LAUNCH(dot_final_kernel<double>, 1, 32, 0, (const double *)scratch, grid, (double *)data_ptr(t));
     }
     scratch_free(scratch);
@@ -626,16 +772,21 @@ dn_status dn_mat_vec_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor
     if (M == 0) return DN_OK;
     const int64_t abs_k = a->stride[1] < 0 ? -a->stride[1] : a->stride[1];
     const int64_t abs_m = a->stride[0] < 0 ? -a->stride[0] : a->stride[0];
-    const int wpr = abs_k <= abs_m ? 1 : 0;
-    int64_t ctas = wpr ? (M + 7) / 8 : (M + 255) / 256;
+    const int esz = dtype_size(t->dtype);
+    int mode = abs_k <= abs_m ? 1 : 0;
+    if (mode == 0) return t->dtype == DN_F32 ? matvec_t_run<float>(t, a, b) : matvec_t_run<double>(t, a, b);
+    if (mode == 1 && a->stride[1] == 1 && b->stride[0] == 1 && (a->stride[0] * esz) % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(data_ptr(a)) & 15) == 0 && (reinterpret_cast<uintptr_t>(data_ptr(b)) & 15) == 0)
+        mode = 2;
+    int64_t ctas = (M + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 16;
     if (ctas > cap) ctas = cap;
     if (t->dtype == DN_F32)
         DN_LAUNCH(matvec_kernel<float>, (unsigned)ctas, 256, 0, (float *)data_ptr(t), t->stride[0], (const float *)data_ptr(a),
-                  a->stride[0], a->stride[1], (const float *)data_ptr(b), b->stride[0], M, K, wpr);
+                  a->stride[0], a->stride[1], (const float *)data_ptr(b), b->stride[0], M, K, mode);
     else
         DN_LAUNCH(matvec_kernel<double>, (unsigned)ctas, 256, 0, (double *)data_ptr(t), t->stride[0], (const double *)data_ptr(a),
-                  a->stride[0], a->stride[1], (const double *)data_ptr(b), b->stride[0], M, K, wpr);
+                  a->stride[0], a->stride[1], (const double *)data_ptr(b), b->stride[0], M, K, mode);
     return launch_status("MatVecDot kernel");
 }
 

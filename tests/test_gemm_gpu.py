@@ -100,6 +100,52 @@ def test_vec_dots(cuda_dev, dtype):
     assert (np.abs(hv - cv) <= tol * (np.abs(at.T.astype(np.float64)) @ np.abs(x.astype(np.float64)))).all()
 
 
+@pytest.mark.parametrize("dtype", [dtypes.DN_F32, dtypes.DN_F64])
+def test_vec_dots_layouts(cuda_dev, dtype):
+    """Every kernel variant of VecVecDot / MatVecDot: 128-bit path and its tail, unaligned bases, strided and
+    reversed operands, transposed matrices with and without K-slices, strided targets."""
+    rng = np.random.default_rng(45)
+    tol = 1e-4 if dtype == dtypes.DN_F32 else 1e-12
+    f64 = lambda v: v.astype(np.float64)
+    for n in (1, 3, 4, 1027, 70001):
+        x, y = rand_array(rng, (n + 3,), dtype, -1, 1), rand_array(rng, (n + 3,), dtype, -1, 1)
+        (hx, cx), (hy, cy) = pair(x), pair(y)
+        for sl_x, sl_y in [((slice(0, n),), (slice(0, n),)), ((slice(1, n + 1),), (slice(0, n),)),
+                           ((slice(3, n + 3),), (slice(2, n + 2),))]:
+            s_h, s_c = float((hx[sl_x] @ hy[sl_y]).Value), float((cx[sl_x] @ cy[sl_y]).Value)
+            assert abs(s_h - s_c) <= tol * float(np.abs(f64(x[sl_x])) @ np.abs(f64(y[sl_y]))) + 1e-30
+    x, y = rand_array(rng, (2000, 2), dtype, -1, 1), rand_array(rng, (2000,), dtype, -1, 1)
+    (hx, cx), (hy, cy) = pair(x), pair(y)
+    s_h, s_c = float((hx[:, 0] @ hy.reverseAxis(0)).Value), float((cx[:, 0] @ cy.reverseAxis(0)).Value)
+    assert abs(s_h - s_c) <= tol * float(np.abs(f64(x[:, 0])) @ np.abs(f64(y[::-1])))
+    for (m, k) in [(5, 7), (64, 4096), (33, 1026), (2048, 300), (1024, 5000)]:
+        a, x2 = rand_array(rng, (m, k), dtype, -1, 1), rand_array(rng, (k, 2), dtype, -1, 1)
+        x = np.ascontiguousarray(x2.reshape(-1))
+        at = np.ascontiguousarray(a.T)
+        (ha, ca), (hat, cat), (hx, cx), (hx2, cx2) = pair(a), pair(at), pair(x), pair(x2)
+        scale = np.abs(f64(a)) @ np.abs(f64(x[:k])) + 1e-30
+        for hm, cm in [(ha, ca), (hat.T, cat.T)]:
+            for hv_, cv_ in [(hx[0:k], cx[0:k])]:
+                hv, cv = f64((hm @ hv_).toNumpy()), f64((cm @ cv_).toNumpy())
+                assert (np.abs(hv - cv) <= tol * scale).all(), (m, k)
+            hv, cv = f64((hm @ hx2[:, 0]).toNumpy()), f64((cm @ cx2[:, 0]).toNumpy())
+            assert (np.abs(hv - cv) <= tol * (np.abs(f64(a)) @ np.abs(f64(x2[:, 0])) + 1e-30)).all(), (m, k, "strided x")
+        if m > 8:  # row / column sub-views: unaligned rows, unaligned leading column
+            for hm, cm, an in [(ha[1:m - 2, 1:k], ca[1:m - 2, 1:k], a[1:m - 2, 1:k]),
+                               (hat.T[1:m - 2, 1:k], cat.T[1:m - 2, 1:k], a[1:m - 2, 1:k]),
+                               (ha.reverseAxis(0), ca.reverseAxis(0), a[::-1, :])]:
+                kk = an.shape[1]
+                hv, cv = f64((hm @ hx[0:kk]).toNumpy()), f64((cm @ cx[0:kk]).toNumpy())
+                assert (np.abs(hv - cv) <= tol * (np.abs(f64(an)) @ np.abs(f64(x[:kk])) + 1e-30)).all(), (m, k, "sub-view")
+        # strided target
+        for cm in (ca, cat.T):
+            tgt = CudaTensor.zeros((m, 2), dtype)
+            tgt[:, 0].FillDot(cm, cx[0:k])
+            got = f64(tgt.toNumpy())
+            want = f64((ha @ hx[0:k]).toNumpy())
+            assert (np.abs(got[:, 0] - want) <= tol * scale).all() and (got[:, 1] == 0).all()
+
+
 def test_unsupported_types(cuda_dev):
     from deepnet_b200.native import NotSupportedException
     a = CudaTensor.zeros((4, 4), dtypes.DN_I32)

@@ -153,6 +153,16 @@ def main():
     m2 = mask.reshape((8192, 8192))
     ti = Tensor.empty((ntrue, 2), dtypes.DN_I64, dev)
     run("C4 trueIdx [8192,8192] p=0.5", N + 16 * ntrue, lambda: ti.Backend.TrueIndices(ti, m2))
+    # A14: VecVecDot / MatVecDot (HBM-bound)
+    tv1, tv2 = torch.randn(1 << 28, device="cuda"), torch.randn(1 << 28, device="cuda")
+    v1, v2 = wrap(tv1), wrap(tv2)
+    sc = Tensor.empty((), dtypes.DN_F32, dev)
+    run("A14 f32 VecVecDot 2^28", 2 * 4 * (1 << 28), lambda: sc.FillDot(v1, v2))
+    tmat, tx = torch.randn(16384, 16384, device="cuda"), torch.randn(16384, device="cuda")
+    mat, xv = wrap(tmat), wrap(tx)
+    yv = Tensor.empty((16384,), dtypes.DN_F32, dev)
+    run("A14 f32 MatVecDot [16384,16384] . [16384]", 4 * (16384 * 16384 + 2 * 16384), lambda: yv.FillDot(mat, xv))
+    run("A14 f32 MatVecDot A.T . x", 4 * (16384 * 16384 + 2 * 16384), lambda: yv.FillDot(mat.T, xv))
     print("launches:", dev.LaunchCount())
 
 
