@@ -55,6 +55,7 @@ struct EwParams {
     int32_t ndims;
     uint32_t n;           // work items in this launch
     uint32_t splat_mask;  // bit k: operand k has innermost stride 0 (VEC mode: load one element and splat)
+    uint32_t wide;        // every access of 32 bytes or more is 32-byte aligned: use 256-bit LDG/STG (sm_100)
 };
 
 struct IndexT {};  // tag type of the virtual index operand; its loaded value is an int64_t position
@@ -69,10 +70,34 @@ struct alignas((N * sizeof(T) >= 16) ? 16 : (N * sizeof(T))) Pack {
     T v[N];
 };
 
+// 256-bit global accesses (sm_100: LDG/STG.E.256). Measured on B200 (tools/fill_probe.cu): a thread that writes
+// its 32 bytes as two adjacent 128-bit stores makes every warp-level store touch half of each 32-byte sector
+// (3.7 TB/s write-only); one 256-bit store per thread writes whole sectors (7.0 TB/s).
+__device__ __forceinline__ void ldg256(const char *addr, uint4 &lo, uint4 &hi) {
+    asm volatile("ld.global.cs.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(addr)
+                 : "memory");
+}
+__device__ __forceinline__ void stg256(char *addr, const uint4 &lo, const uint4 &hi) {
+    asm volatile("st.global.cs.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(addr), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+                 "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
+
 template <class P>
-__device__ __forceinline__ P load_pack(const char *addr) {
+__device__ __forceinline__ P load_pack(const char *addr, bool wide = false) {
     P out;
-    if constexpr (sizeof(P) % 16 == 0) {
+    if constexpr (sizeof(P) % 32 == 0) {
+        uint4 *dst = reinterpret_cast<uint4 *>(&out);
+        if (wide) {
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(P) / 32); ++i) ldg256(addr + 32 * i, dst[2 * i], dst[2 * i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(P) / 16); ++i) dst[i] = __ldcs(reinterpret_cast<const uint4 *>(addr) + i);
+        }
+    } else if constexpr (sizeof(P) % 16 == 0) {
         uint4 *dst = reinterpret_cast<uint4 *>(&out);
 #pragma unroll
         for (int i = 0; i < (int)(sizeof(P) / 16); ++i) dst[i] = __ldcs(reinterpret_cast<const uint4 *>(addr) + i);
@@ -90,8 +115,17 @@ __device__ __forceinline__ P load_pack(const char *addr) {
 }
 
 template <class P>
-__device__ __forceinline__ void store_pack(char *addr, const P &val) {
-    if constexpr (sizeof(P) % 16 == 0) {
+__device__ __forceinline__ void store_pack(char *addr, const P &val, bool wide = false) {
+    if constexpr (sizeof(P) % 32 == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(&val);
+        if (wide) {
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(P) / 32); ++i) stg256(addr + 32 * i, src[2 * i], src[2 * i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(P) / 16); ++i) __stcs(reinterpret_cast<uint4 *>(addr) + i, src[i]);
+        }
+    } else if constexpr (sizeof(P) % 16 == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(&val);
 #pragma unroll
         for (int i = 0; i < (int)(sizeof(P) / 16); ++i) __stcs(reinterpret_cast<uint4 *>(addr) + i, src[i]);
@@ -111,7 +145,7 @@ template <class T, int VEC>
 struct InPack {
     using L = typename LoadedType<T>::type;
     Pack<L, VEC> p;
-    __device__ __forceinline__ void load(const char *addr, bool splat) {
+    __device__ __forceinline__ void load(const char *addr, bool splat, bool wide = false) {
         if constexpr (std::is_same<T, IndexT>::value) {
             const int64_t base = (int64_t)(intptr_t)addr;
 #pragma unroll
@@ -124,14 +158,14 @@ struct InPack {
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) p.v[j] = s.v[0];
             } else {
-                p = load_pack<Pack<T, VEC>>(addr);
+                p = load_pack<Pack<T, VEC>>(addr, wide);
             }
         }
     }
 };
 template <int VEC>
 struct InPack<void, VEC> {
-    __device__ __forceinline__ void load(const char *, bool) {}
+    __device__ __forceinline__ void load(const char *, bool, bool = false) {}
 };
 
 // Functor signature helper: every functor derives from EwSig<Out, In0[, In1[, In2]]>.
@@ -164,6 +198,9 @@ struct EwSig {
     // does not push the widest past 64 bytes
     static constexpr int Vec = ew_pick_vec(MinSize, MaxSize);
     static constexpr bool Tiled = true;  // instantiate the register-transpose kernel for this functor
+    // Packed functors (1-byte bool operators) also provide `uint32_t packed(uint32_t...)` over four elements per
+    // 32-bit word; the vector kernel uses it instead of sixteen byte-wide evaluations per 128-bit access.
+    static constexpr bool Packed = false;
 };
 
 template <int NOPS, int ND>
@@ -210,6 +247,7 @@ __global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ 
     using P2 = InPack<typename F::In2, VEC>;
 
     const uint32_t tile = kEwThreads * U;
+    const bool wide = VEC > 1 && p.wide != 0;
     for (uint64_t base = (uint64_t)blockIdx.x * tile; base < p.n; base += (uint64_t)gridDim.x * tile) {
         P0 a[U];
         P1 b[U];
@@ -222,9 +260,9 @@ __global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ 
                 int64_t off[NOPS];
                 ew_offsets<NOPS, ND>(p, (uint32_t)idx, off);
                 toff[j] = off[0];
-                if constexpr (F::NSRC > 0) a[j].load(p.ptr[1] + off[1], (p.splat_mask >> 1) & 1);
-                if constexpr (F::NSRC > 1) b[j].load(p.ptr[2] + off[2], (p.splat_mask >> 2) & 1);
-                if constexpr (F::NSRC > 2) c[j].load(p.ptr[3] + off[3], (p.splat_mask >> 3) & 1);
+                if constexpr (F::NSRC > 0) a[j].load(p.ptr[1] + off[1], (p.splat_mask >> 1) & 1, wide);
+                if constexpr (F::NSRC > 1) b[j].load(p.ptr[2] + off[2], (p.splat_mask >> 2) & 1, wide);
+                if constexpr (F::NSRC > 2) c[j].load(p.ptr[3] + off[3], (p.splat_mask >> 3) & 1, wide);
             }
         }
 #pragma unroll
@@ -232,14 +270,24 @@ __global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ 
             const uint64_t idx = base + (uint32_t)j * kEwThreads + threadIdx.x;
             if (idx < p.n) {
                 Pack<Out, VEC> r;
+                if constexpr (F::Packed && VEC % 4 == 0) {
+                    uint32_t *wr = reinterpret_cast<uint32_t *>(&r);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    if constexpr (F::NSRC == 0) r.v[e] = f();
-                    else if constexpr (F::NSRC == 1) r.v[e] = f(a[j].p.v[e]);
-                    else if constexpr (F::NSRC == 2) r.v[e] = f(a[j].p.v[e], b[j].p.v[e]);
-                    else r.v[e] = f(a[j].p.v[e], b[j].p.v[e], c[j].p.v[e]);
+                    for (int e = 0; e < VEC / 4; ++e) {
+                        if constexpr (F::NSRC == 1) wr[e] = f.packed(reinterpret_cast<const uint32_t *>(&a[j].p)[e]);
+                        else wr[e] = f.packed(reinterpret_cast<const uint32_t *>(&a[j].p)[e],
+                                              reinterpret_cast<const uint32_t *>(&b[j].p)[e]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        if constexpr (F::NSRC == 0) r.v[e] = f();
+                        else if constexpr (F::NSRC == 1) r.v[e] = f(a[j].p.v[e]);
+                        else if constexpr (F::NSRC == 2) r.v[e] = f(a[j].p.v[e], b[j].p.v[e]);
+                        else r.v[e] = f(a[j].p.v[e], b[j].p.v[e], c[j].p.v[e]);
+                    }
                 }
-                store_pack(p.ptr[0] + toff[j], r);
+                store_pack(p.ptr[0] + toff[j], r, wide);
             }
         }
     }
@@ -479,6 +527,7 @@ void ew_fill_params(EwParams<NOPS> &p, const EwPlan &plan, int vec) {
         if (d < nd) n *= (uint64_t)s;
     }
     p.n = (uint32_t)n;
+    p.wide = vec > 1 ? 1u : 0u;
     for (int k = 0; k < NOPS; ++k) {
         const EwOperand &o = plan.op[k];
         for (int d = 0; d < DN_MAX_DIMS; ++d) {
@@ -488,6 +537,12 @@ void ew_fill_params(EwParams<NOPS> &p, const EwPlan &plan, int vec) {
         }
         if (o.stride[0] == 0) p.splat_mask |= 1u << k;
         p.ptr[k] = o.ptr;
+        // 256-bit accesses need 32-byte alignment of every access this operand makes with packs of >= 32 bytes
+        if (!o.is_index && o.stride[0] != 0 && (int64_t)vec * o.esize >= 32) {
+            if (((uintptr_t)o.ptr) % 32 != 0) p.wide = 0;
+            for (int d = 1; d < nd; ++d)
+                if ((o.stride[d] * o.esize) % 32 != 0) p.wide = 0;
+        }
     }
 }
 

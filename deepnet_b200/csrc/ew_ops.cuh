@@ -41,9 +41,15 @@ DN_LIMITS(int64_t, INT64_MIN, INT64_MAX)
 DN_LIMITS(uint64_t, 0ull, UINT64_MAX)
 #undef DN_LIMITS
 
+// Four bool bytes per 32-bit word: 0x01 in every byte whose input byte is non-zero (bools are normalised on load,
+// KernelCompiler.fs:190-193 marshals them as one byte but foreign memory may hold any non-zero value).
+__device__ __forceinline__ uint32_t bool4_norm(uint32_t w) { return __vcmpne4(w, 0u) & 0x01010101u; }
+
 // ---- unary ---------------------------------------------------------------------------------------------------
 template <class T, int OP>
 struct UnaryF : EwSig<T, T> {
+    static constexpr bool Packed = kIsBool<T>;
+    __device__ __forceinline__ uint32_t packed(uint32_t a) const { return __vcmpeq4(a, 0u) & 0x01010101u; }  // Negate
     __device__ __forceinline__ T operator()(T x) const {
         if constexpr (kIsBool<T>) {
             return bool8(!bool(x));  // Negate, ScalarOps.fs:491-493
@@ -84,6 +90,12 @@ struct UnaryF : EwSig<T, T> {
 // ---- binary --------------------------------------------------------------------------------------------------
 template <class T, int OP>
 struct BinaryF : EwSig<T, T, T> {
+    static constexpr bool Packed = kIsBool<T>;
+    __device__ __forceinline__ uint32_t packed(uint32_t a, uint32_t b) const {
+        if constexpr (OP == DN_AND) return bool4_norm(a) & bool4_norm(b);
+        else if constexpr (OP == DN_OR) return bool4_norm(a | b);
+        else return bool4_norm(a) ^ bool4_norm(b);
+    }
     __device__ __forceinline__ T operator()(T a, T b) const {
         if constexpr (kIsBool<T>) {
             if constexpr (OP == DN_AND) return bool8(bool(a) && bool(b));

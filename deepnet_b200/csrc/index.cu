@@ -5,14 +5,15 @@
 // (CudaBackend.fs:489-492 raise NotSupportedException); their semantics are the host's (ScalarOps.fs:667-707):
 // walk the tensor in LOGICAL row-major order of the view, whatever its strides.
 //
-// Ordered compaction: one primitive shared by TrueIndices, MaskedGet and MaskedSet —
-//   pass 1  every CTA counts the true elements of its tile of 4096 consecutive logical positions
-//           (thread = 16 consecutive positions, one 128-bit load when they are contiguous in memory);
-//   scan    exclusive scan of the per-tile counts (one CTA, they are only N/4096 values);
-//   pass 2  every CTA re-reads its tile (L2-resident for typical masks), ranks its true elements with a
-//           ballot-free register count + warp shuffle scan, and hands (rank, logical position) to a sink:
-//           coordinates (TrueIndices), source -> dense target (MaskedGet), dense values -> target (MaskedSet),
-//           or a plain index list (per-dimension masks, which select a cartesian product: ScalarOps.fs:672-681).
+// Ordered compaction: one single-pass primitive shared by TrueIndices, MaskedGet and MaskedSet. Every CTA draws
+// tiles of 8192 consecutive logical positions from a ticket counter (thread = 16 consecutive positions, one
+// 128-bit load when they are contiguous in memory), ranks its true elements with a register popcount + shuffle
+// scan, obtains the number of true elements in all earlier tiles by decoupled look-back over a 64-bit
+// {status, count} word per tile (the mask is read from HBM exactly once, no count pass, no scan kernel), stages
+// the selected positions in shared memory so that consecutive threads own consecutive ranks, and hands
+// (rank, logical position) to a sink: coordinates (TrueIndices), source -> dense target (MaskedGet), dense
+// values -> target (MaskedSet), or a plain index list (per-dimension masks, which select a cartesian product:
+// ScalarOps.fs:672-681). Sinks are two-phase (load, store) so that four independent loads are in flight per thread.
 #include "ew_ops.cuh"
 
 using namespace dn;
@@ -208,7 +209,8 @@ dn_status validate_gs(const dn_tensor *walked, const dn_tensor *other, const dn_
 // Ordered compaction
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kItems = 16;                          // consecutive logical positions per thread
-constexpr int kTileElems = kIdxThreads * kItems;    // 4096 per CTA
+constexpr int kCompactThreads = 512;
+constexpr int kTileElems = kCompactThreads * kItems;  // 8192 per tile
 
 struct BoolView {           // a bool tensor walked in logical row-major order
     const char *ptr;
@@ -264,94 +266,36 @@ __device__ __forceinline__ uint32_t load_mask_bits(const BoolView &m, uint32_t f
     return bits;
 }
 
-__global__ void __launch_bounds__(kIdxThreads) mask_count_kernel(const __grid_constant__ BoolView m, uint32_t *tile_counts,
-                                                              unsigned long long *total) {
-    __shared__ uint32_t warp_sums[kIdxThreads / 32];
-    if (!tile_counts) {
-        // count only (dn_count_true): keep several 128-bit loads in flight, one block reduction at the very end
-        unsigned long long acc = 0;
-        const uint64_t nchunks = ((uint64_t)m.n + kItems - 1) / kItems;
-        for (uint64_t c = (uint64_t)blockIdx.x * kIdxThreads + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * kIdxThreads * 4) {
-            uint32_t b[4];
+// dn_count_true: several 128-bit loads in flight per thread, one block reduction at the very end.
+__global__ void __launch_bounds__(kIdxThreads) mask_count_kernel(const __grid_constant__ BoolView m, unsigned long long *total) {
+    unsigned long long acc = 0;
+    const uint64_t nchunks = ((uint64_t)m.n + kItems - 1) / kItems;
+    for (uint64_t c = (uint64_t)blockIdx.x * kIdxThreads + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * kIdxThreads * 4) {
+        uint32_t b[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint64_t cc = c + (uint64_t)u * gridDim.x * kIdxThreads;
-                b[u] = cc < nchunks ? load_mask_bits(m, (uint32_t)(cc * kItems)) : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) acc += __popc(b[u]);
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t cc = c + (uint64_t)u * gridDim.x * kIdxThreads;
+            b[u] = cc < nchunks ? load_mask_bits(m, (uint32_t)(cc * kItems)) : 0u;
         }
 #pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-        __shared__ unsigned long long wsum[kIdxThreads / 32];
-        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long t = 0;
-#pragma unroll
-            for (int w = 0; w < kIdxThreads / 32; ++w) t += wsum[w];
-            if (t) atomicAdd(total, t);
-        }
-        return;
+        for (int u = 0; u < 4; ++u) acc += __popc(b[u]);
     }
-    for (uint32_t tile = blockIdx.x; (uint64_t)tile * kTileElems < m.n; tile += gridDim.x) {
-        const uint32_t f0 = tile * kTileElems + threadIdx.x * kItems;
-        uint32_t c = __popc(load_mask_bits(m, f0));
 #pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
-        if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t t = 0;
-#pragma unroll
-            for (int w = 0; w < kIdxThreads / 32; ++w) t += warp_sums[w];
-            tile_counts[tile] = t;
-        }
-        __syncthreads();
-    }
-}
-
-// Exclusive scan of tile counts -> int64 offsets (single CTA; ntiles = N / 4096 is small).
-__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t *counts, int64_t *offsets, uint32_t ntiles) {
-    __shared__ int64_t warp_tot[32];
-    __shared__ int64_t warp_excl[32];
-    __shared__ int64_t chunk_total;
-    __shared__ int64_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
+    for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    __shared__ unsigned long long wsum[kIdxThreads / 32];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < ntiles; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const int64_t v = i < ntiles ? (int64_t)counts[i] : 0;
-        int64_t incl = v;
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const int64_t o = __shfl_up_sync(0xffffffffu, incl, s);
-            if (lane >= s) incl += o;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const int64_t w = warp_tot[lane];
-            int64_t wi = w;
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const int64_t o = __shfl_up_sync(0xffffffffu, wi, s);
-                if (lane >= s) wi += o;
-            }
-            warp_excl[lane] = wi - w;
-            if (lane == 31) chunk_total = wi;
-        }
-        __syncthreads();
-        if (i < ntiles) offsets[i] = carry_s + warp_excl[warp] + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s += chunk_total;
-        __syncthreads();
+        for (int w = 0; w < kIdxThreads / 32; ++w) t += wsum[w];
+        if (t) atomicAdd(total, t);
     }
 }
 
-// Sinks --------------------------------------------------------------------------------------------------------
+// Sinks: `load(rank, f)` fetches what the element needs, `store(rank, f, v)` writes it -------------------------------
 struct CoordSink {  // TrueIndices: t[rank, d] = coordinate d of the element (descriptor dim order)
+    using Value = int;
     char *t;
     int64_t ts0, ts1;  // bytes
     int64_t cap;       // rows available in t
@@ -359,16 +303,17 @@ struct CoordSink {  // TrueIndices: t[rank, d] = coordinate d of the element (de
     int32_t dense;     // t is row-major contiguous and 16-byte aligned: rows of 1 or 2 coordinates are one store
     uint32_t shape[DN_MAX_DIMS];  // innermost-first (the ORIGINAL dims of the view)
     FastDiv div[DN_MAX_DIMS];
-    __device__ __forceinline__ void operator()(int64_t rank, uint32_t f) const {
+    __device__ __forceinline__ Value load(int64_t, uint32_t) const { return 0; }
+    __device__ __forceinline__ void store(int64_t rank, uint32_t f, Value) const {
         if (rank >= cap) return;
         if (dense && nd == 2) {  // the common case (matrix mask): one division, one 128-bit store per row
             const uint32_t q = div[0].div(f);
             const longlong2 row = make_longlong2((long long)q, (long long)(f - q * shape[0]));
-            *reinterpret_cast<longlong2 *>(t + rank * 16) = row;
+            __stcs(reinterpret_cast<longlong2 *>(t + rank * 16), row);
             return;
         }
         if (dense && nd == 1) {
-            *reinterpret_cast<int64_t *>(t + rank * 8) = (int64_t)f;
+            __stcs(reinterpret_cast<long long *>(t + rank * 8), (long long)f);
             return;
         }
         uint32_t rem = f;
@@ -385,42 +330,76 @@ struct CoordSink {  // TrueIndices: t[rank, d] = coordinate d of the element (de
 };
 
 struct IndexListSink {  // sel[rank] = f
+    using Value = int;
     int64_t *sel;
     int64_t cap;
-    __device__ __forceinline__ void operator()(int64_t rank, uint32_t f) const {
+    __device__ __forceinline__ Value load(int64_t, uint32_t) const { return 0; }
+    __device__ __forceinline__ void store(int64_t rank, uint32_t f, Value) const {
         if (rank < cap) sel[rank] = (int64_t)f;
     }
 };
 
 template <class B>
 struct GetSink {  // MaskedGet 1-D: t[rank] = a[f]
+    using Value = B;
     char *t;
     const char *a;
     int64_t ts, as;  // bytes
     int64_t cap;
-    __device__ __forceinline__ void operator()(int64_t rank, uint32_t f) const {
-        if (rank < cap) *reinterpret_cast<B *>(t + rank * ts) = *reinterpret_cast<const B *>(a + (int64_t)f * as);
+    __device__ __forceinline__ Value load(int64_t rank, uint32_t f) const {
+        return rank < cap ? *reinterpret_cast<const B *>(a + (int64_t)f * as) : B(0);
+    }
+    __device__ __forceinline__ void store(int64_t rank, uint32_t, Value v) const {
+        if (rank < cap) *reinterpret_cast<B *>(t + rank * ts) = v;
     }
 };
 
 template <class B>
 struct SetSink {  // MaskedSet 1-D: t[f] = a[rank]
+    using Value = B;
     char *t;
     const char *a;
     int64_t ts, as;
     int64_t cap;  // values available in a
-    __device__ __forceinline__ void operator()(int64_t rank, uint32_t f) const {
-        if (rank < cap) *reinterpret_cast<B *>(t + (int64_t)f * ts) = *reinterpret_cast<const B *>(a + rank * as);
+    __device__ __forceinline__ Value load(int64_t rank, uint32_t) const {
+        return rank < cap ? *reinterpret_cast<const B *>(a + rank * as) : B(0);
+    }
+    __device__ __forceinline__ void store(int64_t rank, uint32_t f, Value v) const {
+        if (rank < cap) *reinterpret_cast<B *>(t + (int64_t)f * ts) = v;
     }
 };
 
+// Tile status word of the decoupled look-back: bits 63..62 = status, bits 61..0 = count.
+constexpr unsigned long long kStAggregate = 1ull << 62;  // count = true elements of this tile only
+constexpr unsigned long long kStPrefix = 2ull << 62;     // count = true elements of tiles 0..this (inclusive)
+constexpr unsigned long long kStValueMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// state[0..ntiles) and *ticket must be zero on entry. Tiles are handed out in ticket order, so every tile a CTA
+// waits on during look-back is owned by a CTA that is already running: no deadlock whatever the grid size.
 template <class Sink>
-__global__ void __launch_bounds__(kIdxThreads) mask_emit_kernel(const __grid_constant__ BoolView m, const int64_t *tile_offsets,
-                                                             const Sink sink) {
-    __shared__ uint32_t warp_sums[kIdxThreads / 32];
+__global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_constant__ BoolView m, unsigned long long *state,
+                                                                 uint32_t *ticket, uint32_t ntiles, const Sink sink) {
+    constexpr int kWarps = kCompactThreads / 32;
+    constexpr int U = 4;
+    __shared__ uint32_t warp_sums[kWarps];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base;
     __shared__ uint32_t staged[kTileElems];  // logical positions of the tile's true elements, in order
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t tile = blockIdx.x; (uint64_t)tile * kTileElems < m.n; tile += gridDim.x) {
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles) return;
         const uint32_t f0 = tile * kTileElems + threadIdx.x * kItems;
         const uint32_t bits = load_mask_bits(m, f0);
         const uint32_t c = __popc(bits);
@@ -434,9 +413,37 @@ __global__ void __launch_bounds__(kIdxThreads) mask_emit_kernel(const __grid_con
         __syncthreads();
         uint32_t before = 0, tile_total = 0;
 #pragma unroll
-        for (int w = 0; w < kIdxThreads / 32; ++w) {
-            if (w < warp) before += warp_sums[w];
-            tile_total += warp_sums[w];
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t ws = warp_sums[w];
+            if (w < warp) before += ws;
+            tile_total += ws;
+        }
+        if (warp == 0) {
+            // publish this tile's aggregate, then look back for the exclusive prefix (warp-wide, 32 tiles per step)
+            if (lane == 0) st_state(state + tile, (tile == 0 ? kStPrefix : kStAggregate) | tile_total);
+            unsigned long long excl = 0;
+            int64_t look = (int64_t)tile - 1;
+            while (look >= 0) {
+                const int64_t idx = look - lane;
+                unsigned long long v;
+                do {
+                    v = idx >= 0 ? ld_state(state + idx) : kStPrefix;
+                } while (__any_sync(0xffffffffu, (v >> 62) == 0));
+                const uint32_t pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                const int first = pm ? __ffs(pm) - 1 : 31;
+                unsigned long long contrib = lane <= first ? (v & kStValueMask) : 0ull;
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, s);
+                excl += contrib;
+                if (pm) break;
+                look -= 32;
+            }
+            if (lane == 0) {
+                if (tile != 0) st_state(state + tile, kStPrefix | (excl + tile_total));
+                s_base = excl;
+            }
+        } else {
+            // the other warps stage while warp 0 looks back
         }
         uint32_t local = before + incl - c;
         uint32_t b = bits;
@@ -446,9 +453,23 @@ __global__ void __launch_bounds__(kIdxThreads) mask_emit_kernel(const __grid_con
             staged[local++] = f0 + j;
         }
         __syncthreads();
-        // consecutive threads emit consecutive ranks: dense-side accesses are fully coalesced
-        const int64_t base = tile_offsets[tile];
-        for (uint32_t i = threadIdx.x; i < tile_total; i += kIdxThreads) sink(base + i, staged[i]);
+        // consecutive threads emit consecutive ranks: dense-side accesses are fully coalesced; U loads in flight
+        const int64_t base = (int64_t)s_base;
+        for (uint32_t i0 = 0; i0 < tile_total; i0 += kCompactThreads * U) {
+            uint32_t f[U];
+            typename Sink::Value v[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const uint32_t i = i0 + j * kCompactThreads + threadIdx.x;
+                f[j] = i < tile_total ? staged[i] : 0xffffffffu;
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (f[j] != 0xffffffffu) v[j] = sink.load(base + i0 + j * kCompactThreads + threadIdx.x, f[j]);
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (f[j] != 0xffffffffu) sink.store(base + i0 + j * kCompactThreads + threadIdx.x, f[j], v[j]);
+        }
         __syncthreads();
     }
 }
@@ -500,26 +521,30 @@ void merge_bool_view(BoolView &v) {
     }
 }
 
-int tiles_grid(uint32_t ntiles) {
-    const int64_t cap = (int64_t)sm_count() * 16;
+int tiles_grid(uint32_t ntiles, int per_sm) {
+    const int64_t cap = (int64_t)sm_count() * per_sm;
     return (int)(ntiles < cap ? (ntiles ? ntiles : 1) : cap);
 }
 
-// Runs count + scan + emit for one bool view.
+// Single-pass ordered compaction of one bool view into `sink`.
 template <class Sink>
 dn_status run_compaction(const BoolView &m, const Sink &sink) {
     if (m.n == 0) return DN_OK;
     const uint32_t ntiles = (uint32_t)(((uint64_t)m.n + kTileElems - 1) / kTileElems);
     void *scratch = nullptr;
-    dn_status st = scratch_alloc((size_t)ntiles * (sizeof(uint32_t) + sizeof(int64_t)) + 16, &scratch);
+    const size_t nbytes = ((size_t)ntiles + 1) * sizeof(unsigned long long);
+    dn_status st = scratch_alloc(nbytes, &scratch);
     if (st != DN_OK) return st;
-    int64_t *offsets = reinterpret_cast<int64_t *>(scratch);
-    uint32_t *counts = reinterpret_cast<uint32_t *>(offsets + ntiles);
-    DN_LAUNCH(mask_count_kernel, tiles_grid(ntiles), kIdxThreads, 0, m, counts, (unsigned long long *)nullptr);
-    DN_LAUNCH(tile_scan_kernel, 1, 1024, 0, counts, offsets, ntiles);
-    DN_LAUNCH((mask_emit_kernel<Sink>), tiles_grid(ntiles), kIdxThreads, 0, m, offsets, sink);
+    cudaError_t e = cudaMemsetAsync(scratch, 0, nbytes, current_stream());
+    if (e != cudaSuccess) {
+        scratch_free(scratch);
+        return cuda_error(e, "compaction scratch");
+    }
+    unsigned long long *state = reinterpret_cast<unsigned long long *>(scratch);
+    uint32_t *ticket = reinterpret_cast<uint32_t *>(state + ntiles);
+    DN_LAUNCH((compact_kernel<Sink>), tiles_grid(ntiles, 4), kCompactThreads, 0, m, state, ticket, ntiles, sink);
     scratch_free(scratch);
-    return launch_status("compaction kernels");
+    return launch_status("compaction kernel");
 }
 
 // Separable gather / scatter through per-dimension index lists (general MaskedGet / MaskedSet).
@@ -706,8 +731,8 @@ dn_status dn_count_true(const dn_tensor *a, int64_t *count) {
     st = scratch_alloc(sizeof(unsigned long long), &scratch);
     if (st != DN_OK) return st;
     DN_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), current_stream()));
-    const uint32_t ntiles = (uint32_t)(((uint64_t)m.n + kTileElems - 1) / kTileElems);
-    DN_LAUNCH(mask_count_kernel, tiles_grid(ntiles), kIdxThreads, 0, m, (uint32_t *)nullptr, (unsigned long long *)scratch);
+    const uint32_t nblocks = (uint32_t)(((uint64_t)m.n + kIdxThreads * kItems - 1) / (kIdxThreads * kItems));
+    DN_LAUNCH(mask_count_kernel, tiles_grid(nblocks, 16), kIdxThreads, 0, m, (unsigned long long *)scratch);
     unsigned long long h = 0;
     cudaError_t e = cudaMemcpyAsync(&h, scratch, sizeof h, cudaMemcpyDeviceToHost, current_stream());
     if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());

@@ -181,6 +181,11 @@ struct AllAnyOp {
     __device__ static void step(State &s, bool8 v, int64_t) { s = IsAll ? (s & (int)bool(v)) : (s | (int)bool(v)); }
     __device__ static State combine(State a, State b) { return IsAll ? (a & b) : (a | b); }
     __device__ static Out finalize(State s) { return bool8(s != 0); }
+    // sixteen bools of one 128-bit load at once
+    __device__ static void packed16(State &s, const uint32_t *w) {
+        if constexpr (IsAll) s &= (int)((__vcmpeq4(w[0], 0u) | __vcmpeq4(w[1], 0u) | __vcmpeq4(w[2], 0u) | __vcmpeq4(w[3], 0u)) == 0u);
+        else s |= (int)((w[0] | w[1] | w[2] | w[3]) != 0u);
+    }
 };
 
 struct CountTrueOp {
@@ -190,7 +195,16 @@ struct CountTrueOp {
     __device__ static void step(State &s, bool8 v, int64_t) { s += bool(v) ? 1 : 0; }
     __device__ static State combine(State a, State b) { return a + b; }
     __device__ static Out finalize(State s) { return s; }
+    __device__ static void packed16(State &s, const uint32_t *w) {
+        // per-byte 0/1 flags of the four words add without carry (at most 4 per byte)
+        const uint32_t t = bool4_norm(w[0]) + bool4_norm(w[1]) + bool4_norm(w[2]) + bool4_norm(w[3]);
+        s += (int64_t)__vsadu4(t, 0u);
+    }
 };
+
+template <class Op> struct HasPacked16 : std::false_type {};
+template <bool IsAll> struct HasPacked16<AllAnyOp<IsAll>> : std::true_type {};
+template <> struct HasPacked16<CountTrueOp> : std::true_type {};
 
 template <class T, bool IsMax>
 struct ArgOp {
@@ -306,6 +320,12 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
                     ridx = r0 + j;
                 }
         } else {
+            if constexpr (HasPacked16<Op>::value) {
+                if (n == VEC) {  // v is a 16-byte aligned Pack
+                    Op::packed16(st, reinterpret_cast<const uint32_t *>(v));
+                    return;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
                 if (j < n) op_step(op, st, v[j], i0 + j);
