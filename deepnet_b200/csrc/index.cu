@@ -209,8 +209,8 @@ dn_status validate_gs(const dn_tensor *walked, const dn_tensor *other, const dn_
 // Ordered compaction
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kItems = 16;                          // consecutive logical positions per thread
-constexpr int kCompactThreads = 512;
-constexpr int kTileElems = kCompactThreads * kItems;  // 8192 per tile
+constexpr int kCompactThreads = 256;
+constexpr int kTileElems = kCompactThreads * kItems * 2;  // 8192 per tile (two chunks per thread)
 
 struct BoolView {           // a bool tensor walked in logical row-major order
     const char *ptr;
@@ -220,6 +220,20 @@ struct BoolView {           // a bool tensor walked in logical row-major order
     FastDiv div[DN_MAX_DIMS];
     int64_t stride[DN_MAX_DIMS];   // bytes
 };
+
+// Bit i of the result = byte i of the 16-byte vector is non-zero. Per word: 0x01 per non-zero byte, then the
+// carry-free multiply 0x01020408 moves byte i's flag to bit 24+i.
+__device__ __forceinline__ uint32_t bool16_to_bits(const uint4 &w) {
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t x = ws[i];
+        const uint32_t nz = ((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) >> 7) & 0x01010101u;
+        bits |= ((nz * 0x01020408u) >> 24) << (4 * i);
+    }
+    return bits;
+}
 
 // Loads the (up to 16) mask bytes of logical positions [f0, f0+16) into bits of a 16-bit word.
 __device__ __forceinline__ uint32_t load_mask_bits(const BoolView &m, uint32_t f0) {
@@ -241,14 +255,7 @@ __device__ __forceinline__ uint32_t load_mask_bits(const BoolView &m, uint32_t f
     const char *a = m.ptr + off;
     uint32_t bits = 0;
     if (cnt == kItems && m.stride[0] == 1 && pos[0] + kItems <= m.shape[0] && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
-        const uint4 w = *reinterpret_cast<const uint4 *>(a);
-        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t nz = __vcmpne4(ws[i], 0u);  // 0xff per non-zero byte
-            bits |= ((nz & 1u) | ((nz >> 7) & 2u) | ((nz >> 14) & 4u) | ((nz >> 21) & 8u)) << (4 * i);
-        }
-        return bits;
+        return bool16_to_bits(*reinterpret_cast<const uint4 *>(a));
     }
     // generic: odometer walk
     for (uint32_t j = 0; j < cnt; ++j) {
@@ -293,29 +300,19 @@ __global__ void __launch_bounds__(kIdxThreads) mask_count_kernel(const __grid_co
     }
 }
 
-// Sinks: `load(rank, f)` fetches what the element needs, `store(rank, f, v)` writes it -------------------------------
-struct CoordSink {  // TrueIndices: t[rank, d] = coordinate d of the element (descriptor dim order)
+// Sinks: `load(rank, f)` fetches what the element needs, `store(rank, f, v)` writes it; the kernel only calls
+// them for ranks below `cap` (rows / values available on the dense side) ------------------------------------------
+struct CoordSink {
     using Value = int;
+    static constexpr bool kLoadNeedsRank = false;
     char *t;
     int64_t ts0, ts1;  // bytes
     int64_t cap;       // rows available in t
     int32_t nd;
-    int32_t dense;     // t is row-major contiguous and 16-byte aligned: rows of 1 or 2 coordinates are one store
     uint32_t shape[DN_MAX_DIMS];  // innermost-first (the ORIGINAL dims of the view)
     FastDiv div[DN_MAX_DIMS];
     __device__ __forceinline__ Value load(int64_t, uint32_t) const { return 0; }
     __device__ __forceinline__ void store(int64_t rank, uint32_t f, Value) const {
-        if (rank >= cap) return;
-        if (dense && nd == 2) {  // the common case (matrix mask): one division, one 128-bit store per row
-            const uint32_t q = div[0].div(f);
-            const longlong2 row = make_longlong2((long long)q, (long long)(f - q * shape[0]));
-            __stcs(reinterpret_cast<longlong2 *>(t + rank * 16), row);
-            return;
-        }
-        if (dense && nd == 1) {
-            __stcs(reinterpret_cast<long long *>(t + rank * 8), (long long)f);
-            return;
-        }
         uint32_t rem = f;
 #pragma unroll
         for (int k = 0; k < DN_MAX_DIMS; ++k) {
@@ -329,43 +326,60 @@ struct CoordSink {  // TrueIndices: t[rank, d] = coordinate d of the element (de
     }
 };
 
+// TrueIndices of a matrix mask into a dense, 16-byte aligned [nTrue, 2] target (the common case): one division and
+// one 128-bit store per row.
+struct CoordSink2D {
+    using Value = int;
+    static constexpr bool kLoadNeedsRank = false;
+    longlong2 *t;
+    int64_t cap;
+    uint32_t ncols;
+    FastDiv div;
+    __device__ __forceinline__ Value load(int64_t, uint32_t) const { return 0; }
+    __device__ __forceinline__ void store(int64_t rank, uint32_t f, Value) const {
+        const uint32_t q = div.div(f);
+        __stcs(t + rank, make_longlong2((long long)q, (long long)(f - q * ncols)));
+    }
+};
+
 struct IndexListSink {  // sel[rank] = f
     using Value = int;
+    static constexpr bool kLoadNeedsRank = false;
     int64_t *sel;
     int64_t cap;
     __device__ __forceinline__ Value load(int64_t, uint32_t) const { return 0; }
-    __device__ __forceinline__ void store(int64_t rank, uint32_t f, Value) const {
-        if (rank < cap) sel[rank] = (int64_t)f;
-    }
+    __device__ __forceinline__ void store(int64_t rank, uint32_t f, Value) const { sel[rank] = (int64_t)f; }
 };
 
 template <class B>
 struct GetSink {  // MaskedGet 1-D: t[rank] = a[f]
     using Value = B;
+    static constexpr bool kLoadNeedsRank = false;  // the source element is known before the rank is
     char *t;
     const char *a;
     int64_t ts, as;  // bytes
     int64_t cap;
-    __device__ __forceinline__ Value load(int64_t rank, uint32_t f) const {
-        return rank < cap ? *reinterpret_cast<const B *>(a + (int64_t)f * as) : B(0);
+    __device__ __forceinline__ Value load(int64_t, uint32_t f) const {
+        return *reinterpret_cast<const B *>(a + (int64_t)f * as);
     }
     __device__ __forceinline__ void store(int64_t rank, uint32_t, Value v) const {
-        if (rank < cap) *reinterpret_cast<B *>(t + rank * ts) = v;
+        *reinterpret_cast<B *>(t + rank * ts) = v;
     }
 };
 
 template <class B>
 struct SetSink {  // MaskedSet 1-D: t[f] = a[rank]
     using Value = B;
+    static constexpr bool kLoadNeedsRank = true;
     char *t;
     const char *a;
     int64_t ts, as;
     int64_t cap;  // values available in a
     __device__ __forceinline__ Value load(int64_t rank, uint32_t) const {
-        return rank < cap ? *reinterpret_cast<const B *>(a + rank * as) : B(0);
+        return *reinterpret_cast<const B *>(a + rank * as);
     }
-    __device__ __forceinline__ void store(int64_t rank, uint32_t f, Value v) const {
-        if (rank < cap) *reinterpret_cast<B *>(t + (int64_t)f * ts) = v;
+    __device__ __forceinline__ void store(int64_t, uint32_t f, Value v) const {
+        *reinterpret_cast<B *>(t + (int64_t)f * ts) = v;
     }
 };
 
@@ -383,94 +397,179 @@ __device__ __forceinline__ void st_state(unsigned long long *p, unsigned long lo
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// state[0..ntiles) and *ticket must be zero on entry. Tiles are handed out in ticket order, so every tile a CTA
-// waits on during look-back is owned by a CTA that is already running: no deadlock whatever the grid size.
-template <class Sink>
-__global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_constant__ BoolView m, unsigned long long *state,
-                                                                 uint32_t *ticket, uint32_t ntiles, const Sink sink) {
+// One CTA per tile; a tile is ROUNDS x 8192 consecutive logical positions (2*ROUNDS 128-bit mask loads per
+// thread, all issued up front). state[0..ntiles) and *ticket must be zero on entry. Tiles are handed out in ticket
+// order, so every tile a CTA waits on during look-back is owned by a CTA that is already running: no deadlock
+// whatever order the hardware dispatches CTAs in. Phases per tile: mask loads -> ranks inside the tile -> publish
+// the tile's count -> per round: stage the selected positions (16-bit offsets) in shared memory, issue the first
+// group of sink loads, [first round: look-back by warp 0, its latency overlaps the loads in flight], stores.
+// ROUNDS = 4 amortises ticket, look-back and their barriers over 32768 positions; ROUNDS = 1 keeps small inputs
+// spread over the machine.
+constexpr int kRoundElems = kTileElems;  // positions staged at a time
+
+template <class Sink, bool FAST, int ROUNDS>
+__global__ void __launch_bounds__(kCompactThreads, ROUNDS == 1 ? 6 : 4) compact_kernel(const __grid_constant__ BoolView m, unsigned long long *state,
+                                                                    uint32_t *ticket, const Sink sink) {
     constexpr int kWarps = kCompactThreads / 32;
+    constexpr int NCH = 2 * ROUNDS;                     // 4096-position chunks per tile
+    constexpr int kChunkElems = kCompactThreads * kItems;
     constexpr int U = 4;
-    __shared__ uint32_t warp_sums[kWarps];
+    __shared__ uint32_t warp_sums[NCH][kWarps];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
-    __shared__ uint32_t staged[kTileElems];  // logical positions of the tile's true elements, in order
+    __shared__ uint16_t staged[kRoundElems];  // round offsets of the round's true elements, in logical order
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= ntiles) return;
-        const uint32_t f0 = tile * kTileElems + threadIdx.x * kItems;
-        const uint32_t bits = load_mask_bits(m, f0);
-        const uint32_t c = __popc(bits);
-        uint32_t incl = c;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tile0 = (uint64_t)tile * (kRoundElems * ROUNDS);
+    uint32_t bits[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const uint64_t f0 = tile0 + c * kChunkElems + threadIdx.x * kItems;
+        if (FAST && f0 + kItems <= m.n) bits[c] = bool16_to_bits(__ldcs(reinterpret_cast<const uint4 *>(m.ptr + f0)));
+        else bits[c] = f0 < m.n ? load_mask_bits(m, (uint32_t)f0) : 0u;
+    }
+    uint32_t excl_in_warp[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const uint32_t cnt = __popc(bits[c]);
+        uint32_t incl = cnt;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
             const uint32_t o = __shfl_up_sync(0xffffffffu, incl, s);
             if (lane >= s) incl += o;
         }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        uint32_t before = 0, tile_total = 0;
+        if (lane == 31) warp_sums[c][warp] = incl;
+        excl_in_warp[c] = incl - cnt;
+    }
+    __syncthreads();
+    uint32_t tile_total = 0;
+    uint32_t local[NCH];      // rank of this thread's first element of chunk c inside its round
+    uint32_t round_total[ROUNDS];
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const uint32_t ws = warp_sums[w];
-            if (w < warp) before += ws;
-            tile_total += ws;
+    for (int r = 0; r < ROUNDS; ++r) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = 2 * r + h;
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const uint32_t ws = warp_sums[c][w];
+                if (w < warp) before += ws;
+                total += ws;
+            }
+            local[c] = acc + before + excl_in_warp[c];
+            acc += total;
         }
+        round_total[r] = acc;
+        tile_total += acc;
+    }
+    if (threadIdx.x == 0) st_state(state + tile, (tile == 0 ? kStPrefix : kStAggregate) | tile_total);
+
+    // Exclusive prefix of this tile by decoupled look-back (warp 0). The chain "prefix published -> visible to the
+    // tiles behind" advances one window per L2 round trip, so the window is 32 * kLook predecessors wide.
+    auto look_back = [&]() {
         if (warp == 0) {
-            // publish this tile's aggregate, then look back for the exclusive prefix (warp-wide, 32 tiles per step)
-            if (lane == 0) st_state(state + tile, (tile == 0 ? kStPrefix : kStAggregate) | tile_total);
+            constexpr int kLook = 4;
             unsigned long long excl = 0;
-            int64_t look = (int64_t)tile - 1;
+            int64_t look = (int64_t)tile - 1;  // nearest predecessor not yet accounted for
             while (look >= 0) {
-                const int64_t idx = look - lane;
-                unsigned long long v;
+                unsigned long long v[kLook];
+                int stop;         // first k whose state ends this lane's walk (a prefix, or not yet published)
+                bool stop_ready;  // ... and that state is a prefix
+                uint32_t stops;
                 do {
-                    v = idx >= 0 ? ld_state(state + idx) : kStPrefix;
-                } while (__any_sync(0xffffffffu, (v >> 62) == 0));
-                const uint32_t pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                const int first = pm ? __ffs(pm) - 1 : 31;
-                unsigned long long contrib = lane <= first ? (v & kStValueMask) : 0ull;
+#pragma unroll
+                    for (int k = 0; k < kLook; ++k) {
+                        const int64_t idx = look - (lane * kLook + k);
+                        v[k] = idx >= 0 ? ld_state(state + idx) : kStPrefix;
+                    }
+                    stop = kLook;
+                    stop_ready = false;
+#pragma unroll
+                    for (int k = kLook - 1; k >= 0; --k)
+                        if ((v[k] >> 62) != 1) {
+                            stop = k;
+                            stop_ready = (v[k] >> 62) == 2;
+                        }
+                    stops = __ballot_sync(0xffffffffu, stop < kLook);
+                    // the nearest stopping state must be a prefix; if it is unpublished, poll again
+                } while (stops && !__shfl_sync(0xffffffffu, stop_ready, __ffs(stops) - 1));
+                const int first = stops ? __ffs(stops) - 1 : 32;
+                unsigned long long contrib = 0;
+#pragma unroll
+                for (int k = 0; k < kLook; ++k)
+                    if (lane < first || (lane == first && k <= stop)) contrib += v[k] & kStValueMask;
 #pragma unroll
                 for (int s = 16; s >= 1; s >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, s);
                 excl += contrib;
-                if (pm) break;
-                look -= 32;
+                if (stops) break;
+                look -= 32 * kLook;
             }
             if (lane == 0) {
                 if (tile != 0) st_state(state + tile, kStPrefix | (excl + tile_total));
                 s_base = excl;
             }
-        } else {
-            // the other warps stage while warp 0 looks back
-        }
-        uint32_t local = before + incl - c;
-        uint32_t b = bits;
-        while (b) {
-            const int j = __ffs(b) - 1;
-            b &= b - 1;
-            staged[local++] = f0 + j;
         }
         __syncthreads();
-        // consecutive threads emit consecutive ranks: dense-side accesses are fully coalesced; U loads in flight
-        const int64_t base = (int64_t)s_base;
-        for (uint32_t i0 = 0; i0 < tile_total; i0 += kCompactThreads * U) {
+        return (int64_t)s_base;
+    };
+
+    int64_t base = 0;
+    bool have_base = false;
+    if constexpr (Sink::kLoadNeedsRank) {
+        base = look_back();
+        have_base = true;
+    }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const uint32_t round0 = (uint32_t)tile0 + (uint32_t)r * kRoundElems;
+        if (r > 0) __syncthreads();  // the previous round's staged offsets are no longer read
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t b = bits[2 * r + h];
+            uint32_t at = local[2 * r + h];
+            const uint32_t off0 = h * kChunkElems + threadIdx.x * kItems;
+#pragma unroll
+            for (int j = 0; j < kItems; ++j)  // predicated, no divergent loop
+                if ((b >> j) & 1u) staged[at++] = (uint16_t)(off0 + j);
+        }
+        __syncthreads();
+        // Consecutive threads own consecutive ranks: dense-side accesses are fully coalesced; U loads in flight.
+        // Index math inside the round is 32-bit; the target capacity is folded into the round's limit once.
+        const uint32_t rt = round_total[r];
+        for (uint32_t i0 = 0; i0 < rt || (i0 == 0 && !have_base); i0 += kCompactThreads * U) {
             uint32_t f[U];
             typename Sink::Value v[U];
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const uint32_t i = i0 + j * kCompactThreads + threadIdx.x;
-                f[j] = i < tile_total ? staged[i] : 0xffffffffu;
+                f[j] = i < rt ? round0 + staged[i] : 0xffffffffu;
+            }
+            if constexpr (!Sink::kLoadNeedsRank) {
+#pragma unroll
+                for (int j = 0; j < U; ++j)
+                    if (f[j] != 0xffffffffu) v[j] = sink.load(0, f[j]);
+                if (!have_base) {  // uniform; overlaps the loads issued above
+                    base = look_back();
+                    have_base = true;
+                }
+            }
+            const int64_t room = sink.cap - base;  // ranks of this round that fit the target
+            const uint32_t lim = room <= 0 ? 0u : (room < (int64_t)rt ? (uint32_t)room : rt);
+            const int64_t rank0 = base + threadIdx.x;
+            if constexpr (Sink::kLoadNeedsRank) {
+#pragma unroll
+                for (int j = 0; j < U; ++j)
+                    if (i0 + j * kCompactThreads + threadIdx.x < lim) v[j] = sink.load(rank0 + (i0 + j * kCompactThreads), f[j]);
             }
 #pragma unroll
             for (int j = 0; j < U; ++j)
-                if (f[j] != 0xffffffffu) v[j] = sink.load(base + i0 + j * kCompactThreads + threadIdx.x, f[j]);
-#pragma unroll
-            for (int j = 0; j < U; ++j)
-                if (f[j] != 0xffffffffu) sink.store(base + i0 + j * kCompactThreads + threadIdx.x, f[j], v[j]);
+                if (i0 + j * kCompactThreads + threadIdx.x < lim) sink.store(rank0 + (i0 + j * kCompactThreads), f[j], v[j]);
         }
-        __syncthreads();
+        base += rt;
     }
 }
 
@@ -530,7 +629,9 @@ int tiles_grid(uint32_t ntiles, int per_sm) {
 template <class Sink>
 dn_status run_compaction(const BoolView &m, const Sink &sink) {
     if (m.n == 0) return DN_OK;
-    const uint32_t ntiles = (uint32_t)(((uint64_t)m.n + kTileElems - 1) / kTileElems);
+    // big inputs: 32768 positions per CTA; small ones: 8192, so that they still spread over the machine
+    const int rounds = (uint64_t)m.n >= (uint64_t)sm_count() * 12 * kTileElems * 4 ? 4 : 1;
+    const uint32_t ntiles = (uint32_t)(((uint64_t)m.n + (uint64_t)kTileElems * rounds - 1) / ((uint64_t)kTileElems * rounds));
     void *scratch = nullptr;
     const size_t nbytes = ((size_t)ntiles + 1) * sizeof(unsigned long long);
     dn_status st = scratch_alloc(nbytes, &scratch);
@@ -542,7 +643,12 @@ dn_status run_compaction(const BoolView &m, const Sink &sink) {
     }
     unsigned long long *state = reinterpret_cast<unsigned long long *>(scratch);
     uint32_t *ticket = reinterpret_cast<uint32_t *>(state + ntiles);
-    DN_LAUNCH((compact_kernel<Sink>), tiles_grid(ntiles, 4), kCompactThreads, 0, m, state, ticket, ntiles, sink);
+    const bool fast = m.nd == 1 && m.stride[0] == 1 && (reinterpret_cast<uintptr_t>(m.ptr) & 15) == 0;
+
+    if (fast && rounds == 4) DN_LAUNCH((compact_kernel<Sink, true, 4>), ntiles, kCompactThreads, 0, m, state, ticket, sink);
+    else if (fast) DN_LAUNCH((compact_kernel<Sink, true, 1>), ntiles, kCompactThreads, 0, m, state, ticket, sink);
+    else if (rounds == 4) DN_LAUNCH((compact_kernel<Sink, false, 4>), ntiles, kCompactThreads, 0, m, state, ticket, sink);
+    else DN_LAUNCH((compact_kernel<Sink, false, 1>), ntiles, kCompactThreads, 0, m, state, ticket, sink);
     scratch_free(scratch);
     return launch_status("compaction kernel");
 }
@@ -750,13 +856,22 @@ dn_status dn_true_indices(const dn_tensor *t, const dn_tensor *a) {
     BoolView m;
     dn_status st = make_bool_view(m, a, "TrueIndices");
     if (st != DN_OK) return st;
+    const bool dense = t->stride[1] == 1 && t->stride[0] == t->shape[1] && (reinterpret_cast<uintptr_t>(data_ptr(t)) & 15) == 0;
+    if (dense && m.nd == 2) {
+        CoordSink2D sink2{reinterpret_cast<longlong2 *>(data_ptr(t)), t->shape[0], m.shape[0], m.div[0]};
+        merge_bool_view(m);
+        return run_compaction(m, sink2);
+    }
+    if (dense && m.nd == 1) {
+        IndexListSink sink1{reinterpret_cast<int64_t *>(data_ptr(t)), t->shape[0]};
+        return run_compaction(m, sink1);
+    }
     CoordSink sink;
     sink.t = data_ptr(t);
     sink.ts0 = t->stride[0] * 8;
     sink.ts1 = t->stride[1] * 8;
     sink.cap = t->shape[0];
     sink.nd = m.nd;
-    sink.dense = (t->stride[1] == 1 && t->stride[0] == t->shape[1] && (reinterpret_cast<uintptr_t>(sink.t) & 15) == 0) ? 1 : 0;
     for (int k = 0; k < DN_MAX_DIMS; ++k) {  // coordinates are reported in the ORIGINAL dims
         sink.shape[k] = m.shape[k];
         sink.div[k] = m.div[k];
