@@ -291,7 +291,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--side", type=int, default=SIDE, help="tensor side (default 16384 = 2^28 elements)")
-    ap.add_argument("--cpu-side", type=int, default=2048, help="side of the bounded CPU sample")
+    ap.add_argument("--cpu-side", type=int, default=4096, help="side of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the C1/C3/C4 side measurements")
     args = ap.parse_args()
@@ -504,6 +504,44 @@ def main():
     e2e_ms = float(t.item())
     e2e_value = step_bytes * world / (e2e_ms * 1e-3) / 1e9
 
+    # ---- sharded reductions (BASELINE.json configs[2]): ArgMaxLastAxis + MaxLastAxis over a
+    # 262144 x 1000 float32 tensor split along dim 0 over the ranks (strong scaling), outputs combined by an NCCL
+    # all-gather; timed on the device, max over ranks. Reported beside the headline.
+    sharded = None
+    try:
+        from deepnet_b200.shard import LeadingAxisSharding, slab
+        TD = {torch.float32: dtypes.DN_F32, torch.int64: dtypes.DN_I64, torch.bool: dtypes.DN_BOOL}
+        sh = LeadingAxisSharding(lambda t: CudaTensor.usingPtr(t.data_ptr(), tuple(t.shape), TD[t.dtype], owner=t),
+                                 torch.device("cuda", local_rank))
+        R3, C3 = 262144, 1000
+        b3, c3 = slab(R3, rank, world)
+        tl = torch.rand(c3, C3, device="cuda") * 100 - 50
+        lg = CudaTensor.usingPtr(tl.data_ptr(), (c3, C3), dtypes.DN_F32, owner=tl)
+
+        def c3_step():
+            sh.reduce_axis("ArgMaxLastAxis", lg, 1, R3)
+            sh.reduce_axis("MaxLastAxis", lg, 1, R3)
+        for _ in range(3):
+            c3_step()
+        barrier()
+        s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps3 = 10
+        s3.record(stream)
+        for _ in range(reps3):
+            c3_step()
+        e3.record(stream)
+        barrier()
+        t3 = torch.tensor([s3.elapsed_time(e3) / reps3], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        ms3 = float(t3.item())
+        nb3 = 2 * R3 * C3 * 4 + R3 * 12
+        sharded = {"workload": f"C3 ArgMaxLastAxis + MaxLastAxis over {R3}x{C3} float32, {world} leading-axis shard(s), "
+                               "outputs all-gathered (NCCL)", "ms": ms3, "GB/s": nb3 / ms3 / 1e6, "scaling": "strong"}
+        del tl, lg
+    except Exception as ex:
+        sharded = {"error": repr(ex)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -522,6 +560,7 @@ def main():
                 "ms_per_step": e2e_ms, "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "sharded_reductions": sharded,
     }
     if world == 1 and not args.no_extra:
         try:

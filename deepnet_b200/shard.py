@@ -86,6 +86,46 @@ class LeadingAxisSharding:
                 out[b:b + c].CopyFrom(parts[r][0:c])
         return out
 
+    def all_gather_ragged(self, local: Tensor) -> Tensor:
+        """Concatenates per-rank tensors whose dim 0 differs from rank to rank (compaction results), in rank order.
+        NCCL has no allgatherv: the counts are all-gathered first, then every rank broadcasts its block into its
+        place of the result."""
+        cnt_t, cnt = self._buffer((1,), dtypes.DN_I64)
+        cnt.FillConst(local.Shape[0])
+        counts = [int(c) for c in self.all_gather_parts(cnt).toNumpy().reshape(-1)]
+        rest = local.Shape[1:]
+        out_t, out = self._buffer((sum(counts),) + rest, local.DataType)
+        row = 1
+        for n in rest:
+            row *= n
+        off = 0
+        for r, c in enumerate(counts):
+            if c > 0:
+                if r == self.rank:
+                    out[off:off + c].CopyFrom(local)
+                    self._sync_compute(local)
+                if self.world > 1:
+                    dist.broadcast(out_t.view(-1)[off * row:(off + c) * row], src=dist.get_global_rank(self.group, r)
+                                   if self.group is not None else r, group=self.group)
+            off += c
+        return out
+
+    # -- ordered compaction (row-major order of the full tensor == rank order of the slabs) -----------------------
+    def true_indices(self, local_mask: Tensor, total_rows: int) -> Tensor:
+        """Tensor.trueIdx of a bool tensor sharded along dim 0: local TrueIndices, dim-0 coordinates shifted by the
+        slab's first row, blocks concatenated in rank order."""
+        base, _ = slab(total_rows, self.rank, self.world)
+        idx = local_mask.trueIdx()                                   # [nTrue_local, nDims]
+        if base != 0 and idx.Shape[0] > 0:
+            col0 = idx[:, 0:1]
+            col0.CopyFrom(col0 + base)
+        return self.all_gather_ragged(idx)
+
+    def masked_get(self, local: Tensor, local_mask: Tensor) -> Tensor:
+        """`a.M(mask)` with a mask of a's full shape, both sharded along dim 0: local MaskedGet, blocks concatenated
+        in rank order (the logical row-major walk of ScalarOps.fs:667-681 visits the slabs in that order)."""
+        return self.all_gather_ragged(local.M(local_mask))
+
     # -- reductions -------------------------------------------------------------------------------------------
     FOLDS = {"SumLastAxis": "sumAxis", "ProductLastAxis": "productAxis", "MinLastAxis": "minAxis",
              "MaxLastAxis": "maxAxis", "AllLastAxis": "allAxis", "AnyLastAxis": "anyAxis"}

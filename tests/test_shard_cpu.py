@@ -74,6 +74,15 @@ def _worker(rank, world, port, out_dir):
         same("whole sum", sh.reduce_axis("SumLastAxis", flat_loc, 0, R * C), flat_full.sumAxis(0))
         # element-wise needs no collective: compute on the slab, gather rows, compare
         same("elementwise + gather rows", sh.all_gather_rows(loc_i * 3 + loc_i, R), full_i * 3 + full_i)
+        # ordered compaction across shards: trueIdx coordinates and MaskedGet values in global row-major order
+        same("trueIdx", sh.true_indices(loc_b, R), full_b.trueIdx())
+        sparse = rng.uniform(0, 1, size=(R, C)) < 0.05
+        sparse[:beg + cnt if rank == 0 else R] &= True
+        same("trueIdx sparse", sh.true_indices(HostTensor.ofNumpy(sparse[beg:beg + cnt]), R), HostTensor.ofNumpy(sparse).trueIdx())
+        same("maskedGet", sh.masked_get(loc_i, loc_b), full_i.M(full_b))
+        none = np.zeros((R, C), dtype=bool)
+        none[R - 1, C - 1] = True   # only the last rank selects anything
+        same("maskedGet one", sh.masked_get(loc_f, HostTensor.ofNumpy(none[beg:beg + cnt])), full_f.M(HostTensor.ofNumpy(none)))
         bad = [n for n, ok in checks if not ok]
         with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as fh:
             fh.write("OK" if not bad else "FAIL: " + "; ".join(bad))

@@ -44,6 +44,10 @@ same("find", sh.reduce_axis("FindLastAxis", loc, 0, R, value=99.0), full.findAxi
 same("whole argmax", sh.reduce_axis("ArgMaxLastAxis", loc.flatten(), 0, R * C), full.flatten().argMaxAxis(0))
 got = sh.reduce_axis("SumLastAxis", loc[:, 10:], 1, R).toNumpy(); want = full[:, 10:].sumAxis(1).toNumpy()
 if not np.allclose(got, want, rtol=1e-3, atol=1e-1): bad.append("sum axis 1")
+mk = rng.uniform(0, 1, size=(R, C)) < 0.3
+fm, lm = CudaTensor.ofNumpy(mk), CudaTensor.ofNumpy(mk[b:b + c])
+same("trueIdx", sh.true_indices(lm, R), fm.trueIdx())
+same("maskedGet", sh.masked_get(loc, lm), full.M(fm))
 dist.barrier()
 sys.stdout.write(f"RANK{rank}_" + ("OK" if not bad else "FAIL " + ";".join(bad)) + "\n"); sys.stdout.flush()
 dist.destroy_process_group()
