@@ -14,6 +14,8 @@
 // (rank, logical position) to a sink: coordinates (TrueIndices), source -> dense target (MaskedGet), dense
 // values -> target (MaskedSet), or a plain index list (per-dimension masks, which select a cartesian product:
 // ScalarOps.fs:672-681). Sinks are two-phase (load, store) so that four independent loads are in flight per thread.
+#include <cstdlib>
+
 #include "ew_ops.cuh"
 
 using namespace dn;
@@ -397,6 +399,52 @@ __device__ __forceinline__ void st_state(unsigned long long *p, unsigned long lo
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Exclusive prefix (number of true elements in all earlier tiles) of `tile` by decoupled look-back; called by ONE
+// full warp after the tile's aggregate was published. Publishes the tile's inclusive prefix. The chain "prefix
+// published -> visible to the tiles behind" advances one window per L2 round trip, so the window is 32 * kLook
+// predecessors wide.
+__device__ __forceinline__ unsigned long long warp_look_back(unsigned long long *state, uint32_t tile, uint32_t tile_total,
+                                                             int lane) {
+    constexpr int kLook = 4;
+    unsigned long long excl = 0;
+    int64_t look = (int64_t)tile - 1;  // nearest predecessor not yet accounted for
+    while (look >= 0) {
+        unsigned long long v[kLook];
+        int stop;         // first k whose state ends this lane's walk (a prefix, or not yet published)
+        bool stop_ready;  // ... and that state is a prefix
+        uint32_t stops;
+        do {
+#pragma unroll
+            for (int k = 0; k < kLook; ++k) {
+                const int64_t idx = look - (lane * kLook + k);
+                v[k] = idx >= 0 ? ld_state(state + idx) : kStPrefix;
+            }
+            stop = kLook;
+            stop_ready = false;
+#pragma unroll
+            for (int k = kLook - 1; k >= 0; --k)
+                if ((v[k] >> 62) != 1) {
+                    stop = k;
+                    stop_ready = (v[k] >> 62) == 2;
+                }
+            stops = __ballot_sync(0xffffffffu, stop < kLook);
+            // the nearest stopping state must be a prefix; if it is unpublished, poll again
+        } while (stops && !__shfl_sync(0xffffffffu, stop_ready, __ffs(stops) - 1));
+        const int first = stops ? __ffs(stops) - 1 : 32;
+        unsigned long long contrib = 0;
+#pragma unroll
+        for (int k = 0; k < kLook; ++k)
+            if (lane < first || (lane == first && k <= stop)) contrib += v[k] & kStValueMask;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, s);
+        excl += contrib;
+        if (stops) break;
+        look -= 32 * kLook;
+    }
+    if (lane == 0 && tile != 0) st_state(state + tile, kStPrefix | (excl + tile_total));
+    return excl;
+}
+
 // One CTA per tile; a tile is ROUNDS x 8192 consecutive logical positions (2*ROUNDS 128-bit mask loads per
 // thread, all issued up front). state[0..ntiles) and *ticket must be zero on entry. Tiles are handed out in ticket
 // order, so every tile a CTA waits on during look-back is owned by a CTA that is already running: no deadlock
@@ -468,50 +516,10 @@ __global__ void __launch_bounds__(kCompactThreads, ROUNDS == 1 ? 6 : 4) compact_
     }
     if (threadIdx.x == 0) st_state(state + tile, (tile == 0 ? kStPrefix : kStAggregate) | tile_total);
 
-    // Exclusive prefix of this tile by decoupled look-back (warp 0). The chain "prefix published -> visible to the
-    // tiles behind" advances one window per L2 round trip, so the window is 32 * kLook predecessors wide.
     auto look_back = [&]() {
         if (warp == 0) {
-            constexpr int kLook = 4;
-            unsigned long long excl = 0;
-            int64_t look = (int64_t)tile - 1;  // nearest predecessor not yet accounted for
-            while (look >= 0) {
-                unsigned long long v[kLook];
-                int stop;         // first k whose state ends this lane's walk (a prefix, or not yet published)
-                bool stop_ready;  // ... and that state is a prefix
-                uint32_t stops;
-                do {
-#pragma unroll
-                    for (int k = 0; k < kLook; ++k) {
-                        const int64_t idx = look - (lane * kLook + k);
-                        v[k] = idx >= 0 ? ld_state(state + idx) : kStPrefix;
-                    }
-                    stop = kLook;
-                    stop_ready = false;
-#pragma unroll
-                    for (int k = kLook - 1; k >= 0; --k)
-                        if ((v[k] >> 62) != 1) {
-                            stop = k;
-                            stop_ready = (v[k] >> 62) == 2;
-                        }
-                    stops = __ballot_sync(0xffffffffu, stop < kLook);
-                    // the nearest stopping state must be a prefix; if it is unpublished, poll again
-                } while (stops && !__shfl_sync(0xffffffffu, stop_ready, __ffs(stops) - 1));
-                const int first = stops ? __ffs(stops) - 1 : 32;
-                unsigned long long contrib = 0;
-#pragma unroll
-                for (int k = 0; k < kLook; ++k)
-                    if (lane < first || (lane == first && k <= stop)) contrib += v[k] & kStValueMask;
-#pragma unroll
-                for (int s = 16; s >= 1; s >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, s);
-                excl += contrib;
-                if (stops) break;
-                look -= 32 * kLook;
-            }
-            if (lane == 0) {
-                if (tile != 0) st_state(state + tile, kStPrefix | (excl + tile_total));
-                s_base = excl;
-            }
+            const unsigned long long excl = warp_look_back(state, tile, tile_total, lane);
+            if (lane == 0) s_base = excl;
         }
         __syncthreads();
         return (int64_t)s_base;
@@ -630,7 +638,10 @@ template <class Sink>
 dn_status run_compaction(const BoolView &m, const Sink &sink) {
     if (m.n == 0) return DN_OK;
     // big inputs: 32768 positions per CTA; small ones: 8192, so that they still spread over the machine
-    const int rounds = (uint64_t)m.n >= (uint64_t)sm_count() * 12 * kTileElems * 4 ? 4 : 1;
+    // (DN_COMPACT_ROUNDS = 1 | 4 forces either configuration: test hook so that both are covered at small sizes)
+    static const int forced = [] { const char *e = getenv("DN_COMPACT_ROUNDS"); return e ? atoi(e) : 0; }();
+    const int rounds = forced == 1 || forced == 4 ? forced
+                                                  : ((uint64_t)m.n >= (uint64_t)sm_count() * 12 * kTileElems * 4 ? 4 : 1);
     const uint32_t ntiles = (uint32_t)(((uint64_t)m.n + (uint64_t)kTileElems * rounds - 1) / ((uint64_t)kTileElems * rounds));
     void *scratch = nullptr;
     const size_t nbytes = ((size_t)ntiles + 1) * sizeof(unsigned long long);
@@ -858,8 +869,10 @@ dn_status dn_true_indices(const dn_tensor *t, const dn_tensor *a) {
     if (st != DN_OK) return st;
     const bool dense = t->stride[1] == 1 && t->stride[0] == t->shape[1] && (reinterpret_cast<uintptr_t>(data_ptr(t)) & 15) == 0;
     if (dense && m.nd == 2) {
-        CoordSink2D sink2{reinterpret_cast<longlong2 *>(data_ptr(t)), t->shape[0], m.shape[0], m.div[0]};
+        const uint32_t ncols = m.shape[0];
+        const FastDiv div = m.div[0];
         merge_bool_view(m);
+        CoordSink2D sink2{reinterpret_cast<longlong2 *>(data_ptr(t)), t->shape[0], ncols, div};
         return run_compaction(m, sink2);
     }
     if (dense && m.nd == 1) {

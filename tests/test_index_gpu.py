@@ -109,6 +109,29 @@ def test_true_idx_and_count(cuda_dev, shape, p):
         assert_same(h[1:, 2:].trueIdx(), c[1:, 2:].trueIdx(), dtypes.DN_I64, what="trueIdx sliced")
 
 
+@pytest.mark.parametrize("shape", [(1024, 1031), (2048, 1024), (70000, 16), (33, 40000)])
+@pytest.mark.parametrize("p", [0.5, 0.03, 1.0])
+def test_true_idx_large_matrix(cuda_dev, shape, p):
+    """>= 2^20 positions (the 32768-positions-per-CTA configuration of the compaction kernel), incl. rows that are
+    not a multiple of 16 long, strided masks and a target with fewer rows than there are true elements."""
+    rng = np.random.default_rng(39)
+    arr = rng.uniform(0, 1, size=shape) < p
+    h, c = pair(arr)
+    want = h.trueIdx()
+    assert_same(want, c.trueIdx(), dtypes.DN_I64, what="trueIdx large")
+    assert_same(h.T.trueIdx(), c.T.trueIdx(), dtypes.DN_I64, what="trueIdx large transposed")
+    assert_same(h[1:, 3:].trueIdx(), c[1:, 3:].trueIdx(), dtypes.DN_I64, what="trueIdx large sliced")
+    # capped target: only the first rows are written, the rest of the buffer keeps its sentinel
+    n = want.Shape[0]
+    if n > 1000:
+        cap = n - 777
+        buf = CudaTensor.ofNumpy(np.full((n, 2), -7, dtype=np.int64))
+        part = buf[0:cap]
+        part.Backend.TrueIndices(part, c)
+        got = buf.toNumpy()
+        assert (got[:cap] == want.toNumpy()[:cap]).all() and (got[cap:] == -7).all()
+
+
 @pytest.mark.parametrize("dtype", ALL_DTYPES)
 def test_masked_get_set_whole_tensor(cuda_dev, dtype):
     rng = np.random.default_rng(36)
@@ -154,3 +177,18 @@ def test_masked_per_dimension(cuda_dev, dtype):
     mT = rng.uniform(0, 1, size=hT.Shape) < 0.5
     hmT, cmT = pair(mT)
     assert_same(hT.M(hmT), cT.M(cmT), dtype, what="MaskedGet permuted view")
+
+
+def test_compaction_with_32768_position_tiles(cuda_dev):
+    """Inputs of >= ~58 M positions use 32768 positions per CTA (4 staging rounds). DN_COMPACT_ROUNDS=4 forces that
+    configuration so the compaction tests above also cover it at sizes the oracle finishes in seconds."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DN_COMPACT_ROUNDS"):
+        pytest.skip("already running under a forced configuration")
+    env = dict(os.environ, DN_COMPACT_ROUNDS="4")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                          "true_idx or masked"], env=env, capture_output=True, text=True, timeout=900,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
