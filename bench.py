@@ -409,7 +409,7 @@ def main():
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the same calls
     # (profiles/r01_*.raw.csv); None for calls that have not been captured
     ncu_traffic = {
-        "single add contiguous": 2.155864e9 + 1.036331e9,      # profiles/r01_ew_add_contig.raw.csv
+        "single add contiguous": 2.147553e9 + 1.041274e9,      # profiles/r01b_ew_add_contig256.raw.csv
         "single add a.T + b": 2.147507e9 + 1.039083e9,         # profiles/r01_ew_xpose_addT.raw.csv
         "single add a[1:,1:] + b[1:,1:]": 2.152425e9 + 1.035520e9,  # profiles/r01_ew_sliced.raw.csv
         "double add a.T + b": 4.295036e9 + 2.110988e9,         # profiles/r01_ew_xpose_f64_addT.raw.csv

@@ -326,6 +326,12 @@ class TensorCudaDevice(ITensorDevice):
         """Cfg.Stream, CudaCfg.fs:25-27."""
         self.api.call("set_stream", stream)
 
+    def GetStream(self) -> int:
+        import ctypes
+        st = ctypes.c_void_p()
+        self.api.call("get_stream", ctypes.byref(st))
+        return int(st.value or 0)
+
     def SetStacktrace(self, enabled: bool) -> None:
         """Cfg.Stacktrace, CudaCfg.fs:33-35."""
         self.api.call("set_check_errors", 1 if enabled else 0)

@@ -55,6 +55,13 @@ class LeadingAxisSharding:
         return t, (w if len(shape) else w.reshape(()))
 
     def _sync_compute(self, x: Tensor) -> None:
+        """Orders the compute device's work before a collective. When the backend launches on torch's current CUDA
+        stream (dn_set_stream(torch stream), as bench.py and the tests do) torch.distributed already orders its
+        NCCL stream after it with an event, and no host synchronisation is needed."""
+        get = getattr(x.Dev, "GetStream", None)
+        if get is not None and self.torch_device.type == "cuda":
+            if get() == torch.cuda.current_stream(self.torch_device).cuda_stream:
+                return
         sync = getattr(x.Dev, "Synchronize", None)
         if sync is not None:
             sync()
@@ -127,6 +134,10 @@ class LeadingAxisSharding:
         return self.all_gather_ragged(local.M(local_mask))
 
     # -- reductions -------------------------------------------------------------------------------------------
+    # result dtype of each member when it differs from the source's (None = same as the source)
+    OUT_DTYPE = {"SumLastAxis": None, "ProductLastAxis": None, "MinLastAxis": None, "MaxLastAxis": None,
+                 "AllLastAxis": None, "AnyLastAxis": None, "CountTrueLastAxis": dtypes.DN_I64,
+                 "ArgMinLastAxis": dtypes.DN_I64, "ArgMaxLastAxis": dtypes.DN_I64, "FindLastAxis": dtypes.DN_I64}
     FOLDS = {"SumLastAxis": "sumAxis", "ProductLastAxis": "productAxis", "MinLastAxis": "minAxis",
              "MaxLastAxis": "maxAxis", "AllLastAxis": "allAxis", "AnyLastAxis": "anyAxis"}
 
@@ -136,6 +147,25 @@ class LeadingAxisSharding:
         local_fn = {**self.FOLDS, "CountTrueLastAxis": "countTrueAxis", "ArgMinLastAxis": "argMinAxis",
                     "ArgMaxLastAxis": "argMaxAxis"}
         if axis != 0:
+            if total_rows % self.world == 0 and local.Shape[0] == total_rows // self.world and member in self.OUT_DTYPE:
+                # equal slabs: every rank reduces straight into its rows of the full result, then ONE in-place
+                # all-gather (send buffer = this rank's block of the receive buffer) combines them
+                out_dt = self.OUT_DTYPE[member] if self.OUT_DTYPE[member] is not None else local.DataType
+                rest = tuple(n for d, n in enumerate(local.Shape) if d != axis)[1:]
+                out_t, out = self._buffer((total_rows,) + rest, out_dt)
+                cnt = local.Shape[0]
+                mine = out[self.rank * cnt:(self.rank + 1) * cnt]
+                if member == "FindLastAxis":
+                    src = Tensor.PrepareAxisReduceSources(mine, axis, local)
+                    src.Backend.FindLastAxis(value, mine, src)
+                else:
+                    mine._fill_axis(member, axis, local, on_src_backend=self.OUT_DTYPE[member] is not None)
+                self._sync_compute(local)
+                if self.world > 1:
+                    flat = out_t.view(-1)
+                    per = flat.numel() // self.world
+                    dist.all_gather_into_tensor(flat, flat[self.rank * per:(self.rank + 1) * per], group=self.group)
+                return out
             part = local.findAxis(value, axis) if member == "FindLastAxis" else getattr(local, local_fn[member])(axis)
             return self.all_gather_rows(part, total_rows)
         base, _ = slab(total_rows, self.rank, self.world)

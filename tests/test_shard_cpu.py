@@ -74,6 +74,18 @@ def _worker(rank, world, port, out_dir):
         same("whole sum", sh.reduce_axis("SumLastAxis", flat_loc, 0, R * C), flat_full.sumAxis(0))
         # element-wise needs no collective: compute on the slab, gather rows, compare
         same("elementwise + gather rows", sh.all_gather_rows(loc_i * 3 + loc_i, R), full_i * 3 + full_i)
+        # equal slabs (100 rows over 2 ranks): the in-place all-gather path of the non-sharded-axis reductions
+        R2 = 100
+        b2, c2 = slab(R2, rank, world)
+        ef, ei, eb = HostTensor.ofNumpy(f[:R2]), HostTensor.ofNumpy(i[:R2]), HostTensor.ofNumpy(b[:R2])
+        lf, li, lb = (HostTensor.ofNumpy(x[b2:b2 + c2]) for x in (f, i, b))
+        for member, fn in [("SumLastAxis", "sumAxis"), ("MaxLastAxis", "maxAxis"), ("ArgMaxLastAxis", "argMaxAxis"),
+                           ("ArgMinLastAxis", "argMinAxis")]:
+            same(f"equal slabs i64 {member}", sh.reduce_axis(member, li, 1, R2), getattr(ei, fn)(1))
+            same(f"equal slabs f32 {member}", sh.reduce_axis(member, lf, 1, R2), getattr(ef, fn)(1),
+                 exact=member != "SumLastAxis")
+        same("equal slabs countTrue", sh.reduce_axis("CountTrueLastAxis", lb, 1, R2), eb.countTrueAxis(1))
+        same("equal slabs find", sh.reduce_axis("FindLastAxis", li, 1, R2, value=7), ei.findAxis(7, 1))
         # ordered compaction across shards: trueIdx coordinates and MaskedGet values in global row-major order
         same("trueIdx", sh.true_indices(loc_b, R), full_b.trueIdx())
         sparse = rng.uniform(0, 1, size=(R, C)) < 0.05

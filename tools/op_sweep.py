@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default="")
     ap.add_argument("--peak", type=float, default=6539.9)
+    ap.add_argument("--filter", default="", help="run only the lines whose name contains this substring")
     args = ap.parse_args()
     dev = CudaTensor.dev()
     dev.Init(0)
@@ -54,6 +55,8 @@ def main():
     lines = []
 
     def run(name, nbytes, fn):
+        if args.filter and args.filter not in name:
+            return
         ms = timeit(fn, args.reps)
         gbs = nbytes / ms / 1e6
         line = f"{name:44s} {nbytes / 1e6:9.1f} MB {ms:8.3f} ms {gbs:8.1f} GB/s {100 * gbs / args.peak:6.1f} %"
