@@ -56,6 +56,7 @@ struct EwParams {
     uint32_t n;           // work items in this launch
     uint32_t splat_mask;  // bit k: operand k has innermost stride 0 (VEC mode: load one element and splat)
     uint32_t wide;        // every access of 32 bytes or more is 32-byte aligned: use 256-bit LDG/STG (sm_100)
+    uint32_t rev_mask;    // bit k: source k has innermost stride -1 (VEC mode: load the pack and reverse it)
 };
 
 struct IndexT {};  // tag type of the virtual index operand; its loaded value is an int64_t position
@@ -145,7 +146,7 @@ template <class T, int VEC>
 struct InPack {
     using L = typename LoadedType<T>::type;
     Pack<L, VEC> p;
-    __device__ __forceinline__ void load(const char *addr, bool splat, bool wide = false) {
+    __device__ __forceinline__ void load(const char *addr, bool splat, bool wide = false, bool rev = false) {
         if constexpr (std::is_same<T, IndexT>::value) {
             const int64_t base = (int64_t)(intptr_t)addr;
 #pragma unroll
@@ -159,13 +160,21 @@ struct InPack {
                 for (int j = 0; j < VEC; ++j) p.v[j] = s.v[0];
             } else {
                 p = load_pack<Pack<T, VEC>>(addr, wide);
+                if (rev) {  // reversed view: addr is the pack's lowest address, element j lives at VEC-1-j
+#pragma unroll
+                    for (int j = 0; j < VEC / 2; ++j) {
+                        const L tmp = p.v[j];
+                        p.v[j] = p.v[VEC - 1 - j];
+                        p.v[VEC - 1 - j] = tmp;
+                    }
+                }
             }
         }
     }
 };
 template <int VEC>
 struct InPack<void, VEC> {
-    __device__ __forceinline__ void load(const char *, bool, bool = false) {}
+    __device__ __forceinline__ void load(const char *, bool, bool = false, bool = false) {}
 };
 
 // Functor signature helper: every functor derives from EwSig<Out, In0[, In1[, In2]]>.
@@ -260,9 +269,9 @@ __global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ 
                 int64_t off[NOPS];
                 ew_offsets<NOPS, ND>(p, (uint32_t)idx, off);
                 toff[j] = off[0];
-                if constexpr (F::NSRC > 0) a[j].load(p.ptr[1] + off[1], (p.splat_mask >> 1) & 1, wide);
-                if constexpr (F::NSRC > 1) b[j].load(p.ptr[2] + off[2], (p.splat_mask >> 2) & 1, wide);
-                if constexpr (F::NSRC > 2) c[j].load(p.ptr[3] + off[3], (p.splat_mask >> 3) & 1, wide);
+                if constexpr (F::NSRC > 0) a[j].load(p.ptr[1] + off[1], (p.splat_mask >> 1) & 1, wide, VEC > 1 && ((p.rev_mask >> 1) & 1));
+                if constexpr (F::NSRC > 1) b[j].load(p.ptr[2] + off[2], (p.splat_mask >> 2) & 1, wide, VEC > 1 && ((p.rev_mask >> 2) & 1));
+                if constexpr (F::NSRC > 2) c[j].load(p.ptr[3] + off[3], (p.splat_mask >> 3) & 1, wide, VEC > 1 && ((p.rev_mask >> 3) & 1));
             }
         }
 #pragma unroll
@@ -507,6 +516,7 @@ __global__ void __launch_bounds__(kEwThreads) ew_xpose_kernel(const __grid_const
 
 // ---- host-side launch logic (non-template parts live in ew_plan.cu) ------------------------------------------
 bool ew_can_vectorize(const EwPlan &plan, int vec, const int *esize, int64_t *tail_elems);
+bool ew_find_peel(const EwPlan &plan, int vec, const int *esize, int64_t *head);
 // Picks dS for the transpose kernel, or returns -1 when it does not apply.
 int ew_pick_tiled_dim(const EwPlan &plan);
 int ew_grid_for(int64_t work_items, int items_per_cta);
@@ -528,6 +538,7 @@ void ew_fill_params(EwParams<NOPS> &p, const EwPlan &plan, int vec) {
     }
     p.n = (uint32_t)n;
     p.wide = vec > 1 ? 1u : 0u;
+    p.rev_mask = 0;
     for (int k = 0; k < NOPS; ++k) {
         const EwOperand &o = plan.op[k];
         for (int d = 0; d < DN_MAX_DIMS; ++d) {
@@ -537,9 +548,13 @@ void ew_fill_params(EwParams<NOPS> &p, const EwPlan &plan, int vec) {
         }
         if (o.stride[0] == 0) p.splat_mask |= 1u << k;
         p.ptr[k] = o.ptr;
+        if (vec > 1 && !o.is_index && o.stride[0] == -1) {  // reversed source: packs are addressed by their lowest byte
+            p.rev_mask |= 1u << k;
+            p.ptr[k] = o.ptr - (int64_t)(vec - 1) * o.esize;
+        }
         // 256-bit accesses need 32-byte alignment of every access this operand makes with packs of >= 32 bytes
         if (!o.is_index && o.stride[0] != 0 && (int64_t)vec * o.esize >= 32) {
-            if (((uintptr_t)o.ptr) % 32 != 0) p.wide = 0;
+            if (((uintptr_t)p.ptr[k]) % 32 != 0) p.wide = 0;
             for (int d = 1; d < nd; ++d)
                 if ((o.stride[d] * o.esize) % 32 != 0) p.wide = 0;
         }
@@ -619,6 +634,22 @@ dn_status ew_run(EwPlan &plan, const F &f) {
                 return ew_launch_strided<F, 1>(tp, f, tail);
             }
             return DN_OK;
+        }
+        int64_t head = 0;
+        if (ew_find_peel(plan, VEC, esize, &head)) {
+            // misaligned rows: vector body + thin scalar head / tail columns
+            const int64_t tail = (plan.shape[0] - head) % VEC;
+            const int64_t body = plan.shape[0] - head - tail;
+            auto columns = [&](int64_t first, int64_t count) {
+                EwPlan sub = plan;
+                for (int k = 0; k < NOPS; ++k) sub.op[k].ptr += first * sub.op[k].stride[0] * sub.op[k].esize;
+                sub.shape[0] = count;
+                return sub;
+            };
+            dn_status st = ew_launch_strided<F, VEC>(columns(head, body), f, body);
+            if (st == DN_OK && head > 0) st = ew_launch_strided<F, 1>(columns(0, head), f, head);
+            if (st == DN_OK && tail > 0) st = ew_launch_strided<F, 1>(columns(head + body, tail), f, tail);
+            return st;
         }
     }
     if constexpr (F::NSRC > 0 && F::Tiled) {

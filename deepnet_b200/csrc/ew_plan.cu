@@ -92,6 +92,12 @@ dn_status ew_make_plan(EwPlan &plan, const dn_tensor *t, const dn_tensor *const 
     return DN_OK;
 }
 
+// Address of the lowest byte that operand k touches for the first work item of a row (reversed sources read
+// downwards from their first element).
+static uintptr_t ew_first_access(const EwOperand &o, int vec, int esize) {
+    return (uintptr_t)o.ptr - (o.stride[0] == -1 ? (uintptr_t)(vec - 1) * esize : 0);
+}
+
 bool ew_can_vectorize(const EwPlan &plan, int vec, const int *esize, int64_t *tail_elems) {
     *tail_elems = 0;
     const int nd = plan.ndims;
@@ -104,16 +110,53 @@ bool ew_can_vectorize(const EwPlan &plan, int vec, const int *esize, int64_t *ta
             if (o.stride[0] != 0 && o.stride[0] != 1) return false;
             continue;
         }
-        if (k == 0 ? o.stride[0] != 1 : (o.stride[0] != 0 && o.stride[0] != 1)) return false;
+        // target: unit stride; sources: unit stride, splat (0) or reversed (-1: the pack is loaded from the
+        // lowest address and reversed in registers)
+        if (k == 0 ? o.stride[0] != 1 : (o.stride[0] != 0 && o.stride[0] != 1 && o.stride[0] != -1)) return false;
         if (o.stride[0] == 0) continue;  // splat: scalar loads, no alignment requirement
         int64_t bytes = (int64_t)vec * esize[k];
         int64_t align = bytes >= 16 ? 16 : bytes;
-        if (((uintptr_t)o.ptr) % align != 0) return false;
+        if (ew_first_access(o, vec, esize[k]) % align != 0) return false;
         for (int d = 1; d < nd; ++d)
             if ((o.stride[d] * esize[k]) % align != 0) return false;
     }
     *tail_elems = tail;
     return true;
+}
+
+// Row peeling: the innermost dim is unit-stride (or splat / reversed) in every operand and the row pitches keep
+// vector alignment, but the rows START misaligned (a.[1.., 1..] views). Finds the number of leading elements h
+// (< vec) after which every operand is aligned — preferably to 32 bytes for the 256-bit path — so that the
+// launcher can run columns [h, h+body) vectorised and the thin head / tail columns through the scalar kernel.
+bool ew_find_peel(const EwPlan &plan, int vec, const int *esize, int64_t *head) {
+    const int nd = plan.ndims;
+    if (plan.shape[0] < 3 * (int64_t)vec) return false;
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0: 32-byte alignment for packs of >= 32 bytes; pass 1: 16 bytes
+        for (int64_t h = 0; h < vec; ++h) {
+            bool ok = true;
+            for (int k = 0; k < plan.nops && ok; ++k) {
+                const EwOperand &o = plan.op[k];
+                if (o.is_index) {
+                    ok = o.stride[0] == 0 || o.stride[0] == 1;
+                    continue;
+                }
+                if (k == 0 ? o.stride[0] != 1 : (o.stride[0] != 0 && o.stride[0] != 1 && o.stride[0] != -1)) ok = false;
+                if (!ok || o.stride[0] == 0) continue;
+                const int64_t bytes = (int64_t)vec * esize[k];
+                const int64_t align = (pass == 0 && bytes >= 32) ? 32 : (bytes >= 16 ? 16 : bytes);
+                EwOperand shifted = o;
+                shifted.ptr += h * o.stride[0] * esize[k];
+                if (ew_first_access(shifted, vec, esize[k]) % align != 0) ok = false;
+                for (int d = 1; d < nd && ok; ++d)
+                    if ((o.stride[d] * esize[k]) % align != 0) ok = false;
+            }
+            if (ok) {
+                *head = h;
+                return true;
+            }
+        }
+    }
+    return false;
 }
 
 int ew_pick_tiled_dim(const EwPlan &plan) {
