@@ -564,8 +564,12 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
             // a row's latency chain is 1/8 as long and small row counts still fill the machine.
             // (measured: with >= one warp per resident slot and rows <= 64 KiB, the state-heavy ops — ordered
             // float Min/Max, (value, index) pairs — run faster warp-per-row; plain folds prefer CTA-per-row)
+            // Warp-per-row leaves the machine partly idle in its last wave of rows: with long rows it needs at
+            // least ~4 waves of resident warps (64 per SM) to keep that tail below ~10 % (measured: [16384,16384]
+            // f32 Max = 1.7 waves ran at 86 % of peak).
             const bool heavy = Op::ordered || sizeof(State) > 8;
-            if (bytes <= 4096 || (heavy && rc >= warps_wanted && bytes <= 65536)) {
+            const bool enough_waves = rc >= (int64_t)sms * 64 * 4 || bytes <= 16384;
+            if (bytes <= 4096 || (heavy && rc >= warps_wanted && bytes <= 65536 && enough_waves)) {
                 p.parts = 1;
                 p.part_len = L;
                 int64_t ctas = (rc + kRedWarps - 1) / kRedWarps;
