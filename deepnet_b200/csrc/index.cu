@@ -472,11 +472,21 @@ __global__ void __launch_bounds__(kCompactThreads, ROUNDS == 1 ? 6 : 4) compact_
     const uint32_t tile = s_tile;
     const uint64_t tile0 = (uint64_t)tile * (kRoundElems * ROUNDS);
     uint32_t bits[NCH];
+    if (FAST && tile0 + (uint64_t)kChunkElems * NCH <= m.n) {
+        // interior tile of a contiguous mask: all 128-bit loads are issued back to back, then converted
+        uint4 w[NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const uint64_t f0 = tile0 + c * kChunkElems + threadIdx.x * kItems;
-        if (FAST && f0 + kItems <= m.n) bits[c] = bool16_to_bits(__ldcs(reinterpret_cast<const uint4 *>(m.ptr + f0)));
-        else bits[c] = f0 < m.n ? load_mask_bits(m, (uint32_t)f0) : 0u;
+        for (int c = 0; c < NCH; ++c)
+            w[c] = __ldcs(reinterpret_cast<const uint4 *>(m.ptr + tile0 + c * kChunkElems + threadIdx.x * kItems));
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) bits[c] = bool16_to_bits(w[c]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const uint64_t f0 = tile0 + c * kChunkElems + threadIdx.x * kItems;
+            if (FAST && f0 + kItems <= m.n) bits[c] = bool16_to_bits(__ldcs(reinterpret_cast<const uint4 *>(m.ptr + f0)));
+            else bits[c] = f0 < m.n ? load_mask_bits(m, (uint32_t)f0) : 0u;
+        }
     }
     uint32_t excl_in_warp[NCH];
 #pragma unroll
