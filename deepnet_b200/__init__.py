@@ -9,9 +9,9 @@ from . import dtypes, layout
 from .backend import (ITensorDevice, ITensorStorage, NativeTensorBackend, TensorCudaBackend, TensorCudaDevice,
                       TensorCudaStorage, TensorStagingDevice)
 from .layout import NotFound, TensorLayout
-from .native import CudaException, NotSupportedException, OutOfCudaMemoryException
+from .native import CudaException, NotSupportedException, OutOfCudaMemoryException, SingularMatrixException
 from .tensor import CudaTensor, NoMask, Tensor
 
 __all__ = ["dtypes", "layout", "Tensor", "CudaTensor", "NoMask", "NotFound", "TensorLayout", "ITensorDevice",
            "ITensorStorage", "NativeTensorBackend", "TensorCudaBackend", "TensorCudaDevice", "TensorCudaStorage",
-           "TensorStagingDevice", "CudaException", "NotSupportedException", "OutOfCudaMemoryException"]
+           "TensorStagingDevice", "CudaException", "NotSupportedException", "OutOfCudaMemoryException", "SingularMatrixException"]

@@ -171,12 +171,13 @@ class NativeTensorBackend:
     def BatchedMatMatDot(self, trgt, src1, src2) -> None:
         self._call("batched_mat_mat_dot", self._d(trgt), self._d(src1), self._d(src2))
 
+    def BatchedInvert(self, trgt, src) -> None:
+        """TensorBackend.fs:142; CudaBackend.fs:451-484. Raises SingularMatrixException."""
+        self._call("batched_invert", self._d(trgt), self._d(src))
+
     # -- not part of the hot path; unsupported on CUDA in the reference too (CudaBackend.fs:486-488) --------
     def BatchedSVD(self, *a):
         raise NotSupportedException("the CUDA tensor backend currently does not support the BatchedSVD operation")
-
-    def BatchedInvert(self, *a):
-        raise NotSupportedException("BatchedInvert is outside the hot path of this backend (SURVEY.md §8f)")
 
     def SymmetricEigenDecomposition(self, *a):
         raise NotSupportedException(

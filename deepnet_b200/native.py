@@ -19,7 +19,7 @@ DN_MAX_DIMS = 8
 
 # dn_status (include/dn_tensor.h) and the exception the reference raises in the same situation.
 DN_OK, DN_ERR_INVALID_ARG, DN_ERR_UNSUPPORTED, DN_ERR_OUT_OF_MEMORY, DN_ERR_INDEX_OUT_OF_RANGE, DN_ERR_CUDA, \
-    DN_ERR_NO_DEVICE, DN_ERR_SHAPE_MISMATCH = range(8)
+    DN_ERR_NO_DEVICE, DN_ERR_SHAPE_MISMATCH, DN_ERR_SINGULAR_MATRIX = range(9)
 
 
 class CudaException(RuntimeError):
@@ -28,6 +28,10 @@ class CudaException(RuntimeError):
 
 class OutOfCudaMemoryException(MemoryError):
     """CudaUtils.fs:183-210."""
+
+
+class SingularMatrixException(ArithmeticError):
+    """Tensor.SingularMatrixException (Tensor/Tensor/Tensor.fs): raised by invert for non-invertible matrices."""
 
 
 class NotSupportedException(NotImplementedError):
@@ -42,6 +46,7 @@ _EXC = {
     DN_ERR_CUDA: CudaException,
     DN_ERR_NO_DEVICE: CudaException,
     DN_ERR_SHAPE_MISMATCH: RuntimeError,  # InvalidOperationException
+    DN_ERR_SINGULAR_MATRIX: SingularMatrixException,
 }
 
 
@@ -97,6 +102,7 @@ _OPERATOR_SIGNATURES = {
     "mat_vec_dot": [_P, _P, _P],
     "mat_mat_dot": [_P, _P, _P],
     "batched_mat_mat_dot": [_P, _P, _P],
+    "batched_invert": [_P, _P],
 }
 
 # device / storage entry points exported only by the product library

@@ -522,6 +522,21 @@ class Tensor:
             raise ValueError(f"Cannot compute dot product between tensors of shapes {a.Shape} and {b.Shape} "
                              f"into tensor of shape {self.Shape}.")
 
+    def FillInvert(self, a: "Tensor") -> None:
+        """Tensor.FillInvert, Tensor.fs:2809-2815."""
+        Tensor.CheckSameStorage(self, a)
+        if a.NDims < 2:
+            raise ValueError(f"Need at least a matrix to invert but got shape {a.Shape}.")
+        a = a.broadcastTo(self.Shape)
+        self.Backend.BatchedInvert(self, a)
+
+    @staticmethod
+    def invert(a: "Tensor") -> "Tensor":
+        """Tensor.invert, Tensor.fs:2836-2839: (batch) inverse of [..., n, n]; SingularMatrixException if singular."""
+        trgt = Tensor.empty(a.Shape, a.DataType, a.Dev)
+        trgt.FillInvert(a)
+        return trgt
+
     def __matmul__(self, b: "Tensor") -> "Tensor":
         """(.*), Tensor.fs:2772-2798."""
         a = self

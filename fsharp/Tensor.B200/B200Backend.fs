@@ -149,7 +149,8 @@ and TensorB200Backend<'T when 'T: (new: unit -> 'T) and 'T: struct and 'T :> Val
         member this.BatchedMatMatDot (t, a, b) =
             let mutable t, a, b = d t, d a, d b in Native.check (Native.dn_batched_mat_mat_dot (&t, &a, &b))
         // outside the hot path (SURVEY.md §8f-4); SVD / eig are unsupported in the reference's CUDA backend as well
-        member this.BatchedInvert (t, a) = raise (NotSupportedException "BatchedInvert is not implemented by the B200 backend")
+        member this.BatchedInvert (t, a) =
+            let mutable t, a = d t, d a in Native.check (Native.dn_batched_invert (&t, &a))
         member this.BatchedSVD (s, uv, a) = raise (NotSupportedException "BatchedSVD is not supported")
         member this.SymmetricEigenDecomposition (p, vals, vecs, a) =
             raise (NotSupportedException "SymmetricEigenDecomposition is not supported")

@@ -19,7 +19,7 @@ type DnDType =
 /// dn_status and the exception raised for it.
 type DnStatus =
     | Ok = 0 | InvalidArg = 1 | Unsupported = 2 | OutOfMemory = 3 | IndexOutOfRange = 4
-    | Cuda = 5 | NoDevice = 6 | ShapeMismatch = 7
+    | Cuda = 5 | NoDevice = 6 | ShapeMismatch = 7 | SingularMatrix = 8
 
 /// dn_tensor — replaces NativeTensor (Tensor/Tensor/Cuda/NativeTensor.fs:50-57). 152 bytes.
 [<Struct; StructLayout(LayoutKind.Sequential)>]
@@ -105,6 +105,8 @@ module Native =
     extern DnStatus dn_mat_mat_dot(DnTensor& t, DnTensor& a, DnTensor& b)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern DnStatus dn_batched_mat_mat_dot(DnTensor& t, DnTensor& a, DnTensor& b)
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern DnStatus dn_batched_invert(DnTensor& t, DnTensor& a)
 
     /// Maps a non-OK status to the exception the reference raises in the same situation (SURVEY.md §8b).
     let check (st: DnStatus) =
@@ -116,4 +118,5 @@ module Native =
             | DnStatus.IndexOutOfRange  -> raise (IndexOutOfRangeException msg)
             | DnStatus.InvalidArg       -> raise (ArgumentException msg)
             | DnStatus.ShapeMismatch    -> raise (InvalidOperationException msg)
+            | DnStatus.SingularMatrix   -> raise (SingularMatrixException msg)
             | _                         -> failwithf "CUDA error: %s" msg      // ManagedCuda.CudaException

@@ -29,6 +29,7 @@ struct IndexOutOfRangeException : std::out_of_range { using std::out_of_range::o
 struct OutOfCudaMemoryException : std::runtime_error { using std::runtime_error::runtime_error; };
 struct CudaException : std::runtime_error { using std::runtime_error::runtime_error; };
 struct InvalidOperationException : std::logic_error { using std::logic_error::logic_error; };
+struct SingularMatrixException : std::logic_error { using std::logic_error::logic_error; };
 struct ArgumentException : std::invalid_argument { using std::invalid_argument::invalid_argument; };
 
 inline void throw_status(dn_status st, const char *msg) {
@@ -40,6 +41,7 @@ inline void throw_status(dn_status st, const char *msg) {
     case DN_ERR_OUT_OF_MEMORY: throw OutOfCudaMemoryException(m);
     case DN_ERR_INVALID_ARG: throw ArgumentException(m);
     case DN_ERR_SHAPE_MISMATCH: throw InvalidOperationException(m);
+    case DN_ERR_SINGULAR_MATRIX: throw SingularMatrixException(m);
     default: throw CudaException(m);
     }
 }
@@ -158,7 +160,7 @@ struct CudaApi {
     DN_FWD(fill_const) DN_FWD(fill_incrementing) DN_FWD(copy) DN_FWD(convert) DN_FWD(unary) DN_FWD(binary) DN_FWD(compare)
     DN_FWD(is_finite) DN_FWD(if_then_else) DN_FWD(reduce_last_axis) DN_FWD(arg_reduce_last_axis) DN_FWD(find_last_axis)
     DN_FWD(gather) DN_FWD(scatter) DN_FWD(count_true) DN_FWD(masked_get) DN_FWD(masked_set) DN_FWD(true_indices)
-    DN_FWD(vec_vec_dot) DN_FWD(mat_vec_dot) DN_FWD(mat_mat_dot) DN_FWD(batched_mat_mat_dot)
+    DN_FWD(vec_vec_dot) DN_FWD(mat_vec_dot) DN_FWD(mat_mat_dot) DN_FWD(batched_mat_mat_dot) DN_FWD(batched_invert)
 #undef DN_FWD
 };
 
@@ -213,6 +215,10 @@ struct Backend {
     }
     template <class TT, class TA, class TB> static void BatchedMatMatDot(const TT &t, const TA &a, const TB &b) {
         auto x = d(t), y = d(a), z = d(b); Api::check(Api::batched_mat_mat_dot(&x, &y, &z));
+    }
+    // BatchedInvert (TensorBackend.fs:142)
+    template <class TT, class TA> static void BatchedInvert(const TT &t, const TA &a) {
+        auto x = d(t), y = d(a); Api::check(Api::batched_invert(&x, &y));
     }
     template <class TT, class TA, class TB> static void MatVecDot(const TT &t, const TA &a, const TB &b) {
         auto x = d(t), y = d(a), z = d(b); Api::check(Api::mat_vec_dot(&x, &y, &z));
@@ -395,6 +401,14 @@ class Tensor {
             return t;
         }
         throw ArgumentException("Cannot compute dot product between tensors of these shapes.");
+    }
+
+    // invert (Tensor.fs:2836-2839)
+    Tensor invert() const {
+        if (NDims() < 2) throw ArgumentException("Need at least a matrix to invert.");
+        Tensor t(Shape());
+        B::BatchedInvert(t, *this);
+        return t;
     }
 
   private:

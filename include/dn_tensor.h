@@ -47,7 +47,8 @@ typedef enum dn_status {
     DN_ERR_INDEX_OUT_OF_RANGE = 4, /* IndexOutOfRangeException "invalid index during gather or scatter"     */
     DN_ERR_CUDA = 5,               /* CudaException                                                         */
     DN_ERR_NO_DEVICE = 6,          /* CudaException "Cannot create CUDA context" (CudaBackend.fs:28-38)     */
-    DN_ERR_SHAPE_MISMATCH = 7      /* InvalidOperationException                                             */
+    DN_ERR_SHAPE_MISMATCH = 7,     /* InvalidOperationException                                             */
+    DN_ERR_SINGULAR_MATRIX = 8     /* SingularMatrixException "cannot invert singular matrix"               */
 } dn_status;
 
 /* Tensor view descriptor: replaces NativeTensor {Ptr; Offset; Shape; Stride} (NativeTensor.fs:50-57). */
@@ -209,6 +210,12 @@ dn_status dn_mat_vec_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor
 /* MatMatDot / BatchedMatMatDot (TensorBackend.fs:139-140; CudaBackend.fs:410-449): t[..,M,N] = a[..,M,K]·b[..,K,N]. */
 dn_status dn_mat_mat_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b);
 dn_status dn_batched_mat_mat_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b);
+
+/* BatchedInvert (TensorBackend.fs:142; CudaBackend.fs:451-484; host HostBackend.fs:548-577 = LAPACK getrf + getri):
+ * t[..., n, n] = inverse of a[..., n, n], f32 / f64, any strides; t and a may be the same view. Partial pivoting.
+ * Blocking (the reference synchronises on cuBLAS' info array, CudaBackend.fs:467-476): returns
+ * DN_ERR_SINGULAR_MATRIX when a pivot is exactly zero. */
+dn_status dn_batched_invert(const dn_tensor *t, const dn_tensor *a);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Multi-GPU combine steps for leading-axis sharding (new; the reference has no multi-GPU path — SURVEY.md §8e).

@@ -1112,3 +1112,86 @@ dn_status dno_mat_vec_dot(const dn_tensor *t, const dn_tensor *a, const dn_tenso
 }
 
 }  // extern "C"
+
+// BatchedInvert (HostBackend.fs:548-577): copy the source into the target, then per matrix LAPACKE_?getrf (LU with
+// partial pivoting: largest magnitude in the column, first occurrence — LAPACK dgetf2 / idamax) followed by
+// LAPACKE_?getri. MKL itself is not in the reference tree (SURVEY.md §8c "third-party arithmetic"); its published
+// algorithm is restated: unblocked right-looking LU, then A^-1 from  U x = L^-1 P e_j  column by column. info > 0
+// (an exactly zero pivot) = SingularMatrixException. Computed in the element type, like LAPACK.
+template <class T>
+static dn_status invert_impl(const dn_tensor *t, const dn_tensor *a) {
+    const int nd = t->ndims;
+    const int64_t n = t->shape[nd - 1];
+    int64_t batch = 1;
+    for (int d = 0; d < nd - 2; ++d) batch *= t->shape[d];
+    const T *ap = (const T *)a->base + a->offset;
+    T *tp = (T *)t->base + t->offset;
+    std::vector<T> lu((size_t)(n * n)), inv((size_t)(n * n)), col((size_t)n);
+    std::vector<int64_t> piv((size_t)n);
+    for (int64_t bidx = 0; bidx < batch; ++bidx) {
+        int64_t rem = bidx, ao = 0, to = 0;
+        for (int d = nd - 3; d >= 0; --d) {
+            const int64_t p = rem % t->shape[d];
+            rem /= t->shape[d];
+            ao += p * a->stride[d];
+            to += p * t->stride[d];
+        }
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t j = 0; j < n; ++j) lu[(size_t)(i * n + j)] = ap[ao + i * a->stride[nd - 2] + j * a->stride[nd - 1]];
+        // getrf
+        for (int64_t k = 0; k < n; ++k) {
+            int64_t p = k;
+            T best = std::fabs(lu[(size_t)(k * n + k)]);
+            for (int64_t i = k + 1; i < n; ++i) {
+                const T v = std::fabs(lu[(size_t)(i * n + k)]);
+                if (v > best) { best = v; p = i; }
+            }
+            piv[(size_t)k] = p;
+            if (!(best > T(0))) return fail(DN_ERR_SINGULAR_MATRIX, "cannot invert singular matrix");
+            if (p != k)
+                for (int64_t j = 0; j < n; ++j) std::swap(lu[(size_t)(k * n + j)], lu[(size_t)(p * n + j)]);
+            const T pivot = lu[(size_t)(k * n + k)];
+            for (int64_t i = k + 1; i < n; ++i) {
+                const T f = lu[(size_t)(i * n + k)] / pivot;
+                lu[(size_t)(i * n + k)] = f;
+                for (int64_t j = k + 1; j < n; ++j) lu[(size_t)(i * n + j)] -= f * lu[(size_t)(k * n + j)];
+            }
+        }
+        // getri: column j of the inverse solves L U x = P e_j
+        for (int64_t j = 0; j < n; ++j) {
+            for (int64_t i = 0; i < n; ++i) col[(size_t)i] = T(i == j ? 1 : 0);
+            for (int64_t k = 0; k < n; ++k) std::swap(col[(size_t)k], col[(size_t)piv[(size_t)k]]);
+            for (int64_t i = 0; i < n; ++i) {
+                T acc = col[(size_t)i];
+                for (int64_t k = 0; k < i; ++k) acc -= lu[(size_t)(i * n + k)] * col[(size_t)k];
+                col[(size_t)i] = acc;
+            }
+            for (int64_t i = n - 1; i >= 0; --i) {
+                T acc = col[(size_t)i];
+                for (int64_t k = i + 1; k < n; ++k) acc -= lu[(size_t)(i * n + k)] * col[(size_t)k];
+                col[(size_t)i] = acc / lu[(size_t)(i * n + i)];
+            }
+            for (int64_t i = 0; i < n; ++i) inv[(size_t)(i * n + j)] = col[(size_t)i];
+        }
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t j = 0; j < n; ++j) tp[to + i * t->stride[nd - 2] + j * t->stride[nd - 1]] = inv[(size_t)(i * n + j)];
+    }
+    return DN_OK;
+}
+
+extern "C" {
+
+dn_status dno_batched_invert(const dn_tensor *t, const dn_tensor *a) {
+    if (!valid(t) || !valid(a)) return fail(DN_ERR_INVALID_ARG, "batched_invert: bad argument");
+    if (t->dtype != a->dtype || (t->dtype != DN_F32 && t->dtype != DN_F64))
+        return fail(DN_ERR_UNSUPPORTED, "this operation is only supported for floating point numbers");
+    if (t->ndims < 2 || t->ndims != a->ndims || t->shape[t->ndims - 1] != t->shape[t->ndims - 2])
+        return fail(DN_ERR_SHAPE_MISMATCH, "batched_invert: need [..., n, n]");
+    for (int d = 0; d < t->ndims; ++d)
+        if (t->shape[d] != a->shape[d]) return fail(DN_ERR_SHAPE_MISMATCH, "batched_invert: shapes differ");
+    for (int d = 0; d < t->ndims; ++d)
+        if (t->shape[d] == 0) return DN_OK;
+    return t->dtype == DN_F32 ? invert_impl<float>(t, a) : invert_impl<double>(t, a);
+}
+
+}  // extern "C"

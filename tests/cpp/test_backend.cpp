@@ -37,6 +37,7 @@ DNO(vec_vec_dot, const dn_tensor *, const dn_tensor *, const dn_tensor *)
 DNO(mat_vec_dot, const dn_tensor *, const dn_tensor *, const dn_tensor *)
 DNO(mat_mat_dot, const dn_tensor *, const dn_tensor *, const dn_tensor *)
 DNO(batched_mat_mat_dot, const dn_tensor *, const dn_tensor *, const dn_tensor *)
+DNO(batched_invert, const dn_tensor *, const dn_tensor *)
 #undef DNO
 }
 
@@ -52,7 +53,7 @@ struct OracleApi {
     DN_FWD(fill_const) DN_FWD(fill_incrementing) DN_FWD(copy) DN_FWD(convert) DN_FWD(unary) DN_FWD(binary) DN_FWD(compare)
     DN_FWD(is_finite) DN_FWD(if_then_else) DN_FWD(reduce_last_axis) DN_FWD(arg_reduce_last_axis) DN_FWD(find_last_axis)
     DN_FWD(gather) DN_FWD(scatter) DN_FWD(count_true) DN_FWD(masked_get) DN_FWD(masked_set) DN_FWD(true_indices)
-    DN_FWD(vec_vec_dot) DN_FWD(mat_vec_dot) DN_FWD(mat_mat_dot) DN_FWD(batched_mat_mat_dot)
+    DN_FWD(vec_vec_dot) DN_FWD(mat_vec_dot) DN_FWD(mat_mat_dot) DN_FWD(batched_mat_mat_dot) DN_FWD(batched_invert)
 #undef DN_FWD
 };
 
@@ -114,6 +115,11 @@ Results run_suite() {
     TD ii = TD::ofVector({1.1, 0.1, 0.1, 0.1, 1.1, 0.1, 0.1, 0.1, 1.1}, {3, 3});
     expect(close(dbl(h.dot(ii).toVector()), {0.3, 1.3, 2.3, 4.2, 5.2, 6.2, 8.1, 9.1, 10.1, 12, 13, 14, 15.9, 16.9, 17.9}, 1e-12, 1e-12),
            id + " h .* i (Guide-Operations.md:127-147)");
+    TD inv_in = TD::ofVector({1.0, 2.0, 3.0, 4.0}, {2, 2});
+    expect(close(dbl(inv_in.invert().toVector()), {-2.0, 1.0, 1.5, -0.5}, 1e-12, 1e-12), id + " invert (Tensor.fs:2821-2825)");
+    bool threw = false;
+    try { TD::ofVector({1, 0, 0, 1, 2, 0, 1, 0, 0}, {3, 3}).invert(); } catch (const dnhost::SingularMatrixException &) { threw = true; }
+    expect(threw, id + " invert singular matrix raises (BaseTests.fs:205-211)");
 
     // --- seeded workload on views, returned for host-vs-CUDA comparison ---
     std::mt19937_64 gen(99);
@@ -141,6 +147,11 @@ Results run_suite() {
     r["masked"] = dbl(A.M(A.compare(DN_GREATER, Bm)).toVector());
     r["trueidx"] = dbl(A.compare(DN_GREATER, Bm).trueIdx().toVector());
     r["dot"] = dbl(A.dot(At).toVector());  // [67,129] . [129,67]
+    {
+        std::vector<float> sq(3 * 40 * 40);
+        for (size_t i = 0; i < sq.size(); ++i) sq[i] = uni(gen) / 50.f + ((i % (40 * 40)) % 41 == 0 ? 21.f : 0.f);
+        r["invert"] = dbl(TF::ofVector(sq, {3, 40, 40}).invert().toVector());
+    }
     A.FillMultiply(A, Bm);                  // in place (Guide-Operations.md:112-117)
     r["inplace"] = dbl(A.toVector());
     return r;
@@ -158,6 +169,7 @@ int main(int argc, char **argv) {
             if (k == "sin") rtol = 1e-5;
             if (k == "sum1" || k == "sum0") { rtol = 1e-3; atol = 0.05; }
             if (k == "dot") { rtol = 1e-2; atol = 25.0; }  // TF32 tensor cores, |a|.|b| ~ 8e4 per element
+            if (k == "invert") { rtol = 1e-4; atol = 1e-6; }
             expect(close(cuda[k], kv.second, rtol, atol), "cuda vs host: " + k);
         }
     }

@@ -71,6 +71,7 @@ def run_case(case, make):
     elif op == "sum": return t["a"].sum()
     elif op == "all": return t["a"].all()
     elif op == "dot": r = t["a"] @ t["b"]
+    elif op == "invert": r = Tensor.invert(t["a"])
     else: raise KeyError(op)
     return r.toNumpy()
 

@@ -22,3 +22,23 @@ def test_cuda_matches_reference_docs(cuda_dev, case):
     if case["op"] == "dot" and False:
         pytest.skip()
     check_case(case, run_case(case, CudaTensor.ofNumpy))
+
+
+def test_oracle_invert_against_numpy():
+    """The oracle's getrf/getri restatement (HostBackend.fs:548-577) against numpy's LAPACK on random batches, the
+    reference's own invert tests (Tensor.Test/BaseTests.fs:162-211) and the singular-matrix error."""
+    import numpy as np
+    import pytest
+    from deepnet_b200 import SingularMatrixException, Tensor
+    from oracle.host_tensor import HostTensor
+    rng = np.random.default_rng(123)
+    for npdt, tol in ((np.float64, 1e-10), (np.float32, 2e-4)):
+        for shape in [(4, 4), (2, 4, 3, 3), (3, 40, 40)]:
+            m = (rng.uniform(-1, 1, size=shape) + np.eye(shape[-1]) * 2).astype(npdt)
+            got = Tensor.invert(HostTensor.ofNumpy(m)).toNumpy()
+            want = np.linalg.inv(m.astype(np.float64))
+            assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max())
+            back = Tensor.invert(Tensor.invert(HostTensor.ofNumpy(m))).toNumpy()
+            assert np.abs(back - m).max() <= 10 * tol
+    with pytest.raises(SingularMatrixException):
+        Tensor.invert(HostTensor.ofNumpy(np.array([[1.0, 0.0, 0.0], [1.0, 2.0, 0.0], [1.0, 0.0, 0.0]])))
