@@ -430,28 +430,56 @@ dn_status gemm_f32(float *c, int64_t cm, int64_t cn, const float *a, int64_t am,
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kDT = 64, kDK = 16;
 
-__global__ void __launch_bounds__(256) gemm_f64_kernel(double *c, int64_t cm, int64_t cn, const double *a, int64_t am, int64_t ak,
-                                                      const double *b, int64_t bk, int64_t bn, int M, int N, int K) {
-    __shared__ double sa[kDK][kDT + 1], sb[kDK][kDT + 1];
+// Batch decomposition for the SIMT kernel: blockIdx.z (+ z0) -> element offsets of the three operands.
+struct SimtBatch {
+    int32_t ndims;
+    uint32_t shape[DN_MAX_DIMS];   // innermost batch dim first
+    FastDiv div[DN_MAX_DIMS];
+    int64_t cs[DN_MAX_DIMS], as[DN_MAX_DIMS], bs[DN_MAX_DIMS];  // elements; 0 = broadcast
+    uint32_t z0;
+};
+
+// Shared-memory tiled SIMT GEMM (64 x 64 tile, 4 x 4 per thread), one launch for a whole batch. float64 always
+// runs here (B200 tensor cores have no fp64 MMA worth the name); float32 runs here for batches of SMALL matrices,
+// where a tcgen05 launch + two tensor maps per batch element (the reference: cuBLAS gemmBatched over pointer
+// arrays, CudaBackend.fs:429-449) would be launch-bound — and the result is exact fp32 rather than tf32.
+template <class T>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(T *c, int64_t cm, int64_t cn, const T *a, int64_t am, int64_t ak,
+                                                       const T *b, int64_t bk, int64_t bn, int M, int N, int K,
+                                                       const __grid_constant__ SimtBatch batch) {
+    __shared__ T sa[kDK][kDT + 1], sb[kDK][kDT + 1];
+    {
+        uint32_t rem = blockIdx.z + batch.z0;
+#pragma unroll
+        for (int d = 0; d < DN_MAX_DIMS; ++d) {
+            if (d >= batch.ndims) break;
+            const uint32_t q = batch.div[d].div(rem);
+            const int64_t x = rem - q * batch.shape[d];
+            c += x * batch.cs[d];
+            a += x * batch.as[d];
+            b += x * batch.bs[d];
+            rem = q;
+        }
+    }
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * kDT, n0 = blockIdx.x * kDT;
-    double acc[4][4] = {};
+    T acc[4][4] = {};
     for (int k0 = 0; k0 < K; k0 += kDK) {
         for (int i = threadIdx.x; i < kDT * kDK; i += 256) {
             // choose the faster-varying index to follow the operand's contiguous axis
             int mm, kk;
             if (ak == 1) { kk = i % kDK; mm = i / kDK; } else { mm = i % kDT; kk = i / kDT; }
             const int gm = m0 + mm, gk = k0 + kk;
-            sa[kk][mm] = (gm < M && gk < K) ? a[(int64_t)gm * am + (int64_t)gk * ak] : 0.0;
+            sa[kk][mm] = (gm < M && gk < K) ? a[(int64_t)gm * am + (int64_t)gk * ak] : T(0);
             int nn, kb;
             if (bk == 1) { kb = i % kDK; nn = i / kDK; } else { nn = i % kDT; kb = i / kDT; }
             const int gn = n0 + nn, gk2 = k0 + kb;
-            sb[kb][nn] = (gn < N && gk2 < K) ? b[(int64_t)gk2 * bk + (int64_t)gn * bn] : 0.0;
+            sb[kb][nn] = (gn < N && gk2 < K) ? b[(int64_t)gk2 * bk + (int64_t)gn * bn] : T(0);
         }
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < kDK; ++kk) {
-            double av[4], bv[4];
+            T av[4], bv[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { av[i] = sa[kk][ty * 4 + i]; bv[i] = sb[kk][tx * 4 + i]; }
 #pragma unroll
@@ -470,14 +498,41 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(double *c, int64_t cm, in
         }
 }
 
-dn_status gemm_f64(double *c, int64_t cm, int64_t cn, const double *a, int64_t am, int64_t ak, const double *b, int64_t bk,
-                   int64_t bn, int64_t M, int64_t N, int64_t K) {
+// One launch (per 65535 batch elements) for the whole batch. `bt`/`ba`/`bb`: batch strides, innermost batch dim first.
+template <class T>
+dn_status gemm_simt(T *c, int64_t cm, int64_t cn, const T *a, int64_t am, int64_t ak, const T *b, int64_t bk, int64_t bn,
+                    int64_t M, int64_t N, int64_t K, int nbd, const int64_t *bshape, const int64_t *bt, const int64_t *ba,
+                    const int64_t *bb) {
     if (M == 0 || N == 0) return DN_OK;
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return set_error(DN_ERR_UNSUPPORTED, "MatMatDot: extent exceeds 2^31-1");
-    dim3 grid((unsigned)((N + kDT - 1) / kDT), (unsigned)((M + kDT - 1) / kDT));
-    if (grid.y > 65535) return set_error(DN_ERR_UNSUPPORTED, "MatMatDot f64: M too large");
-    DN_LAUNCH(gemm_f64_kernel, grid, 256, 0, c, cm, cn, a, am, ak, b, bk, bn, (int)M, (int)N, (int)K);
-    return launch_status("f64 GEMM kernel");
+    SimtBatch batch;
+    batch.ndims = nbd;
+    batch.z0 = 0;
+    int64_t nbatch = 1;
+    for (int d = 0; d < DN_MAX_DIMS; ++d) {
+        const bool on = d < nbd;
+        batch.shape[d] = on ? (uint32_t)bshape[d] : 1;
+        batch.div[d].init(batch.shape[d]);
+        batch.cs[d] = on ? bt[d] : 0;
+        batch.as[d] = on ? ba[d] : 0;
+        batch.bs[d] = on ? bb[d] : 0;
+        if (on) nbatch *= bshape[d];
+    }
+    if (nbatch == 0) return DN_OK;
+    if (nbatch >= (1ll << 31)) return set_error(DN_ERR_UNSUPPORTED, "BatchedMatMatDot: more than 2^31-1 matrices");
+    dim3 grid((unsigned)((N + kDT - 1) / kDT), (unsigned)((M + kDT - 1) / kDT), 1);
+    if (grid.y > 65535) return set_error(DN_ERR_UNSUPPORTED, "MatMatDot (SIMT path): M too large");
+    for (int64_t z0 = 0; z0 < nbatch; z0 += 65535) {
+        grid.z = (unsigned)(nbatch - z0 < 65535 ? nbatch - z0 : 65535);
+        batch.z0 = (uint32_t)z0;
+        DN_LAUNCH((gemm_simt_kernel<T>), grid, 256, 0, c, cm, cn, a, am, ak, b, bk, bn, (int)M, (int)N, (int)K, batch);
+    }
+    return launch_status("SIMT GEMM kernel");
+}
+
+dn_status gemm_f64(double *c, int64_t cm, int64_t cn, const double *a, int64_t am, int64_t ak, const double *b, int64_t bk,
+                   int64_t bn, int64_t M, int64_t N, int64_t K) {
+    return gemm_simt<double>(c, cm, cn, a, am, ak, b, bk, bn, M, N, K, 0, nullptr, nullptr, nullptr, nullptr);
 }
 
 dn_status check_mm(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b, int nd, const char *what) {
@@ -709,6 +764,29 @@ dn_status dn_batched_mat_mat_dot(const dn_tensor *t, const dn_tensor *a, const d
     if (st != DN_OK) return st;
     int64_t nbatch = 1;
     for (int d = 0; d < nd - 2; ++d) nbatch *= t->shape[d];
+    const int64_t M = a->shape[nd - 2], K = a->shape[nd - 1], N = b->shape[nd - 1];
+    // float64, and float32 batches of small matrices (below 2^27 multiply-adds each — measured: 64 x 256^3 runs at
+    // 3 TFLOP/s as per-element tcgen05 launches, launch- and tensor-map-bound): ONE launch of the SIMT kernel
+    if (nbatch > 1 && (t->dtype == DN_F64 || M * N * K < ((int64_t)1 << 27))) {
+        int64_t bshape[DN_MAX_DIMS], bt[DN_MAX_DIMS], ba[DN_MAX_DIMS], bb[DN_MAX_DIMS];
+        int nbd = 0;
+        for (int d = nd - 3; d >= 0; --d) {  // innermost batch dim first; broadcast batch dims have stride 0
+            bshape[nbd] = t->shape[d];
+            bt[nbd] = t->stride[d];
+            ba[nbd] = a->stride[d];
+            bb[nbd] = b->stride[d];
+            ++nbd;
+        }
+        if (t->dtype == DN_F32)
+            return gemm_simt<float>(reinterpret_cast<float *>(data_ptr(t)), t->stride[nd - 2], t->stride[nd - 1],
+                                    reinterpret_cast<const float *>(data_ptr(a)), a->stride[nd - 2], a->stride[nd - 1],
+                                    reinterpret_cast<const float *>(data_ptr(b)), b->stride[nd - 2], b->stride[nd - 1], M, N, K,
+                                    nbd, bshape, bt, ba, bb);
+        return gemm_simt<double>(reinterpret_cast<double *>(data_ptr(t)), t->stride[nd - 2], t->stride[nd - 1],
+                                 reinterpret_cast<const double *>(data_ptr(a)), a->stride[nd - 2], a->stride[nd - 1],
+                                 reinterpret_cast<const double *>(data_ptr(b)), b->stride[nd - 2], b->stride[nd - 1], M, N, K,
+                                 nbd, bshape, bt, ba, bb);
+    }
     for (int64_t bi = 0; bi < nbatch; ++bi) {
         int64_t rem = bi, to = 0, ao = 0, bo = 0;
         for (int d = nd - 3; d >= 0; --d) {

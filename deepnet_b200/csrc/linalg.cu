@@ -6,8 +6,9 @@
 // like the host backend: HostBackend.fs:552-554) by Gauss-Jordan elimination with partial (row) pivoting — the
 // same pivot rule as LAPACK's getrf (largest magnitude in the column, first occurrence), so well-conditioned
 // results agree with the host's getrf + getri to rounding. Matrices up to 200 KiB live in shared memory for the
-// whole elimination; larger ones are eliminated in place in global memory (L2-resident). Singular matrices (an
-// exactly zero pivot, LAPACK info > 0) raise DN_ERR_SINGULAR_MATRIX = SingularMatrixException.
+// whole elimination (one launch for the whole batch); larger ones are eliminated in global memory with one launch
+// pair per pivot step (pivot + row exchange per matrix, then a rank-1 update spread over the whole GPU). Singular
+// matrices (an exactly zero pivot, LAPACK info > 0) raise DN_ERR_SINGULAR_MATRIX = SingularMatrixException.
 #include "ew_ops.cuh"
 
 using namespace dn;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(kInvThreads) batched_invert_kernel(const __gri
     }
     T *M = reinterpret_cast<T *>(p.t) + off;
     int *piv = piv_global + (int64_t)blockIdx.x * n;
-    if (p.use_smem) {
+    {
         T *W = reinterpret_cast<T *>(smem_raw);
         const int ld = n | 1;  // odd leading dimension: column walks are bank-conflict free
         for (int e = threadIdx.x; e < n * n; e += kInvThreads) {
@@ -143,10 +144,129 @@ __global__ void __launch_bounds__(kInvThreads) batched_invert_kernel(const __gri
             const int i = e / n, j = e - i * n;
             M[(int64_t)i * p.row_stride + (int64_t)j * p.col_stride] = W[i * ld + j];
         }
-    } else {
-        // in place in global memory; requires a row-major dense matrix (the host wrapper guarantees it)
-        gauss_jordan<T>(M, n, p.row_stride, piv, p.singular, (int)blockIdx.x);
     }
+}
+
+// ---- matrices too large for shared memory: one launch pair per pivot step, the whole GPU per step -------------
+__device__ __forceinline__ int64_t inv_batch_offset(const InvParams &p, uint32_t b) {
+    uint32_t rem = b;
+    int64_t off = 0;
+#pragma unroll
+    for (int d = 0; d < DN_MAX_DIMS; ++d) {
+        if (d >= p.nbatch_dims) break;
+        const uint32_t q = p.bdiv[d].div(rem);
+        off += (int64_t)(rem - q * p.bshape[d]) * p.bstride[d];
+        rem = q;
+    }
+    return off;
+}
+
+// Step k, part 1 (one CTA per matrix): pivot search in column k, row exchange, scaling of the pivot row, and a copy
+// of column k (the elimination factors) into colk so that part 2 has no read-after-write hazard on that column.
+template <class T>
+__global__ void __launch_bounds__(kInvThreads) invert_pivot_kernel(const __grid_constant__ InvParams p, int *piv_global, T *colk_global, int k) {
+    if (*reinterpret_cast<volatile int *>(p.singular)) return;
+    __shared__ int s_p;
+    __shared__ T s_pivinv;
+    __shared__ T s_best[kInvThreads / 32];
+    __shared__ int s_widx[kInvThreads / 32];
+    const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    T *W = reinterpret_cast<T *>(p.t) + inv_batch_offset(p, blockIdx.x);
+    const int64_t ld = p.row_stride;
+    int *piv = piv_global + (int64_t)blockIdx.x * n;
+    T *colk = colk_global + (int64_t)blockIdx.x * n;
+    T best = T(-1);
+    int bi = n;
+    for (int i = k + tid; i < n; i += kInvThreads) {
+        const T v = abs_of(W[i * ld + k]);
+        if (v > best) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const T ob = __shfl_xor_sync(0xffffffffu, best, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { s_best[warp] = best; s_widx[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        T b = s_best[0];
+        int q = s_widx[0];
+        for (int w = 1; w < kInvThreads / 32; ++w)
+            if (s_best[w] > b || (s_best[w] == b && s_widx[w] < q)) { b = s_best[w]; q = s_widx[w]; }
+        s_p = q;
+        piv[k] = q;
+        if (!(b > T(0))) {
+            atomicCAS(p.singular, 0, (int)blockIdx.x + 1);
+            s_p = -1;
+        } else {
+            s_pivinv = T(1) / W[q * ld + k];
+        }
+    }
+    __syncthreads();
+    const int q = s_p;
+    if (q < 0) return;
+    const T pivinv = s_pivinv;
+    for (int j = tid; j < n; j += kInvThreads) {  // exchange rows k and q, scale the new row k
+        const T top = W[q * ld + j];
+        if (q != k) W[q * ld + j] = W[k * ld + j];
+        W[k * ld + j] = j == k ? pivinv : top * pivinv;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kInvThreads) colk[i] = W[i * ld + k];  // after the exchange; colk[k] is unused
+}
+
+// Step k, part 2 (grid: column blocks x row blocks x matrices): W[i][j] -= colk[i] * W[k][j]; W[i][k] = -colk[i] / pivot.
+template <class T>
+__global__ void __launch_bounds__(kInvThreads) invert_eliminate_kernel(const __grid_constant__ InvParams p, const T *colk_global, int k) {
+    if (*reinterpret_cast<volatile int *>(p.singular)) return;
+    const int n = p.n;
+    T *W = reinterpret_cast<T *>(p.t) + inv_batch_offset(p, blockIdx.z);
+    const int64_t ld = p.row_stride;
+    const T *colk = colk_global + (int64_t)blockIdx.z * n;
+    const int j = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int i0 = blockIdx.y * 32 + (threadIdx.x >> 6) * 8;
+    if (j >= n) return;
+    const T r = W[k * ld + j];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u;
+        if (i < n && i != k) {
+            const T f = colk[i];
+            W[i * ld + j] = j == k ? -f * r : W[i * ld + j] - f * r;
+        }
+    }
+}
+
+// Undo the row exchanges as column exchanges in reverse order (one CTA per matrix).
+template <class T>
+__global__ void __launch_bounds__(kInvThreads) invert_unpivot_kernel(const __grid_constant__ InvParams p, const int *piv_global) {
+    if (*reinterpret_cast<volatile int *>(p.singular)) return;
+    const int n = p.n;
+    T *W = reinterpret_cast<T *>(p.t) + inv_batch_offset(p, blockIdx.x);
+    const int64_t ld = p.row_stride;
+    const int *piv = piv_global + (int64_t)blockIdx.x * n;
+    // a thread owns whole rows, so the exchanges of one row need no synchronisation between steps
+    for (int i = threadIdx.x; i < n; i += kInvThreads)
+        for (int k = n - 1; k >= 0; --k) {
+            const int q = piv[k];
+            if (q != k) {
+                const T a = W[i * ld + k];
+                W[i * ld + k] = W[i * ld + q];
+                W[i * ld + q] = a;
+            }
+        }
+}
+
+template <class T>
+void invert_stepwise(const InvParams &p, int64_t batch, int *piv, T *colk) {
+    const int n = p.n;
+    const dim3 egrid((unsigned)((n + 63) / 64), (unsigned)((n + 31) / 32), (unsigned)batch);
+    for (int k = 0; k < n; ++k) {
+        DN_LAUNCH((invert_pivot_kernel<T>), (unsigned)batch, kInvThreads, 0, p, piv, colk, k);
+        DN_LAUNCH((invert_eliminate_kernel<T>), egrid, kInvThreads, 0, p, colk, k);
+    }
+    DN_LAUNCH((invert_unpivot_kernel<T>), (unsigned)batch, kInvThreads, 0, p, piv);
 }
 
 }  // namespace
@@ -210,8 +330,9 @@ extern "C" dn_status dn_batched_invert(const dn_tensor *t, const dn_tensor *a) {
         p.bstride[p.nbatch_dims] = work.stride[d];
         ++p.nbatch_dims;
     }
-    void *aux = nullptr;  // [singular flag | pivots]
-    st = scratch_alloc(sizeof(int) * (size_t)(batch * n + 4), &aux);
+    void *aux = nullptr;  // [singular flag | pivots | column copies of the stepwise path]
+    const size_t piv_bytes = (sizeof(int) * (size_t)(batch * n + 4) + 15) / 16 * 16;
+    st = scratch_alloc(piv_bytes + (use_smem ? 0 : (size_t)batch * n * esize), &aux);
     if (st != DN_OK) {
         scratch_free(scratch);
         return st;
@@ -221,7 +342,16 @@ extern "C" dn_status dn_batched_invert(const dn_tensor *t, const dn_tensor *a) {
     int *piv = reinterpret_cast<int *>(aux) + 4;
     const size_t dyn = use_smem ? smem_bytes : 0;
     cudaError_t e = cudaSuccess;
-    if (t->dtype == DN_F32) {
+    if (!use_smem) {
+        if (batch > 65535) {
+            scratch_free(aux);
+            scratch_free(scratch);
+            return set_error(DN_ERR_UNSUPPORTED, "BatchedInvert: more than 65535 matrices of this size");
+        }
+        char *colk = reinterpret_cast<char *>(aux) + piv_bytes;
+        if (t->dtype == DN_F32) invert_stepwise<float>(p, batch, piv, reinterpret_cast<float *>(colk));
+        else invert_stepwise<double>(p, batch, piv, reinterpret_cast<double *>(colk));
+    } else if (t->dtype == DN_F32) {
         if (dyn > 48 * 1024) e = cudaFuncSetAttribute(batched_invert_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e == cudaSuccess) DN_LAUNCH((batched_invert_kernel<float>), (unsigned)batch, kInvThreads, dyn, p, piv);
     } else {

@@ -82,6 +82,41 @@ def test_batched_and_broadcast(cuda_dev, dtype):
 
 
 @pytest.mark.parametrize("dtype", [dtypes.DN_F32, dtypes.DN_F64])
+def test_batched_many_small_and_large(cuda_dev, dtype):
+    """Batches of small matrices run as ONE launch of the SIMT kernel (exact fp32 / fp64 accumulation): compared
+    with numpy's batched matmul at fp32/fp64 rounding, incl. strided views, a broadcast batch operand and more
+    than 65535 matrices; batches of large f32 matrices keep the per-element tcgen05 path."""
+    rng = np.random.default_rng(46)
+    npdt = dtypes.to_numpy(dtype)
+    rtol = 2e-5 if dtype == dtypes.DN_F32 else 1e-12
+
+    def check(ca, cb, a, b, what):
+        want = np.matmul(a.astype(np.float64), b.astype(np.float64))
+        scale = np.matmul(np.abs(a).astype(np.float64), np.abs(b).astype(np.float64)) + 1e-30
+        got = (ca @ cb).toNumpy().astype(np.float64)
+        assert got.shape == want.shape and (np.abs(got - want) <= rtol * scale).all(), what
+
+    a, b = rand_array(rng, (1000, 8, 5), dtype, -1, 1), rand_array(rng, (1000, 5, 9), dtype, -1, 1)
+    check(CudaTensor.ofNumpy(a), CudaTensor.ofNumpy(b), a, b, "1000 x [8,5].[5,9]")
+    a, b = rand_array(rng, (7, 3, 65, 70), dtype, -1, 1), rand_array(rng, (1, 3, 70, 130), dtype, -1, 1)
+    ca, cb = CudaTensor.ofNumpy(a), CudaTensor.ofNumpy(b)
+    check(ca, cb.broadcastTo((7, 3, 70, 130)), a, np.broadcast_to(b, (7, 3, 70, 130)), "broadcast batch dim")
+    # transposed matrices inside the batch (K-major vs MN-major operands) and a sliced batch
+    at = rand_array(rng, (5, 40, 33), dtype, -1, 1)
+    bt = rand_array(rng, (5, 21, 40), dtype, -1, 1)
+    check(CudaTensor.ofNumpy(at).swapDim(1, 2)[1:4], CudaTensor.ofNumpy(bt).swapDim(1, 2)[1:4],
+          np.swapaxes(at, 1, 2)[1:4], np.swapaxes(bt, 1, 2)[1:4], "transposed views")
+    a, b = rand_array(rng, (70000, 2, 3), dtype, -1, 1), rand_array(rng, (70000, 3, 2), dtype, -1, 1)
+    check(CudaTensor.ofNumpy(a), CudaTensor.ofNumpy(b), a, b, "70000 matrices (two launches)")
+    if dtype == dtypes.DN_F32:  # large matrices per batch element: tcgen05 per element, tf32 tolerance
+        a, b = rand_array(rng, (2, 600, 520), dtype, -1, 1), rand_array(rng, (2, 520, 560), dtype, -1, 1)
+        (ha, ca), (hb, cb) = pair(a), pair(b)
+        hc, cc = ha @ hb, ca @ cb
+        for i in range(2):
+            check_mm(hc[i], cc[i], a[i], b[i], dtype, f"large batch element {i}")
+
+
+@pytest.mark.parametrize("dtype", [dtypes.DN_F32, dtypes.DN_F64])
 def test_vec_dots(cuda_dev, dtype):
     rng = np.random.default_rng(44)
     a, x, y = rand_array(rng, (300, 1000), dtype, -1, 1), rand_array(rng, (1000,), dtype, -1, 1), \
