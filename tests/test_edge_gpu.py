@@ -79,8 +79,13 @@ def test_error_conventions(cuda_dev):
         a.Backend.Add(a, a, CudaTensor.zeros((4, 5), dtypes.DN_F64))   # operand types differ
     with pytest.raises(NotSupportedException):
         CudaTensor.zeros((3,), dtypes.DN_BOOL) + CudaTensor.zeros((3,), dtypes.DN_BOOL)
-    with pytest.raises(NotSupportedException):
+    with pytest.raises(RuntimeError):           # InvalidOperationException: [4, 5] is not a (batch of) square matrices
         a.Backend.BatchedInvert(a, a)
+    with pytest.raises(NotSupportedException):  # unsupported on CUDA in the reference too (CudaBackend.fs:486-488)
+        a.Backend.BatchedSVD(a, a, a)
+    ii = CudaTensor.zeros((3, 3), dtypes.DN_I32)
+    with pytest.raises(NotSupportedException):  # "only supported for floating point numbers" (HostBackend.fs:549-550)
+        ii.Backend.BatchedInvert(ii, ii)
     bc = a[0:1, :].broadcastTo((4, 5))
     with pytest.raises(ValueError):             # a broadcast view cannot be a target
         bc.FillAdd(a, a)
