@@ -89,3 +89,51 @@ def test_error_conventions(cuda_dev):
     bc = a[0:1, :].broadcastTo((4, 5))
     with pytest.raises(ValueError):             # a broadcast view cannot be a target
         bc.FillAdd(a, a)
+
+
+def test_concurrent_threads_with_their_own_streams(cuda_dev):
+    """SURVEY §8b "Threading": any thread may call, Cfg.Stream is thread-local (CudaCfg.fs:16,25-27). Four threads,
+    each on its own stream, run element-wise, reduction, compaction, matmul and invert calls concurrently (ctypes
+    releases the GIL during the native calls); every result must equal the single-threaded oracle's."""
+    import threading
+    import torch
+    from deepnet_b200 import Tensor
+    from oracle.host_tensor import HostTensor
+
+    def work(seed):
+        rng = np.random.default_rng(seed)
+        f = rng.uniform(-50, 50, size=(300, 257)).astype(np.float32)
+        i = rng.integers(-1000, 1000, size=(300, 257)).astype(np.int64)
+        sq = (rng.uniform(-1, 1, size=(8, 12, 12)) + 8 * np.eye(12)).astype(np.float64)
+        out = {}
+        for name, mk in (("host", HostTensor.ofNumpy), ("cuda", CudaTensor.ofNumpy)):
+            a, b, m = mk(f), mk(i), mk(sq)
+            out[name] = ((a.T + a.T.reverseAxis(0)).toNumpy(), (b * 3 - b.T.T).sumAxis(0).toNumpy(),
+                         b.M(b.gt(0)).toNumpy(), b.gt(500).trueIdx().toNumpy(), a.argMaxAxis(1).toNumpy(),
+                         Tensor.invert(m).toNumpy(), (m @ m).toNumpy())
+        return out
+
+    results, errors = {}, []
+
+    def runner(k):
+        try:
+            stream = torch.cuda.Stream()
+            cuda_dev.SetStream(stream.cuda_stream)
+            for rep in range(3):
+                results[(k, rep)] = work(1000 + 10 * k + rep)
+            cuda_dev.Synchronize()
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=runner, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert len(results) == 12
+    for key, out in results.items():
+        for h, c in zip(out["host"][:5], out["cuda"][:5]):
+            assert h.shape == c.shape and (h == c).all(), key
+        np.testing.assert_allclose(out["cuda"][5], out["host"][5], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(out["cuda"][6], out["host"][6], rtol=1e-10, atol=1e-10)
