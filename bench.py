@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 
 import numpy as np
 
+NCU_F64_ADD_TRAFFIC = 4.294980e9 + 2.118896e9  # profiles/r01c_ew_add_contig256_f64.raw.csv
 METRIC = "elementwise/reduction HBM GB/s (% of B200 peak) at 1/2/4/8 GPUs vs HostTensor"
 SIDE = 16384  # 2^28 elements per tensor
 
@@ -59,19 +60,22 @@ def build_cases(T, dt, a, b, c, row, col, mask, has_sin: bool):
     nm = dtypes.NAMES[dt]
     cs, as_, bs = c[1:, 1:], a[1:, 1:], b[1:, 1:]
     ar0, ar1, aT = a.reverseAxis(0), a.reverseAxis(1), a.T
+    T_ = {"single": "float", "double": "double", "int32": "int"}[nm]
+    k_add = f"ew_kernel<BinaryF<{T_},ADD>,VEC={32 // s}> (256-bit vector kernel)"
+    k_addT = f"ew_xpose_kernel<BinaryF<{T_},ADD>> (register transpose)"
     cases = [
-        (f"{nm} add contiguous", 3 * N * s, lambda: c.FillAdd(a, b)),
-        (f"{nm} add a.T + b", 3 * N * s, lambda: c.FillAdd(aT, b)),
-        (f"{nm} add a + row[1,C]", (2 * N + C) * s, lambda: c.FillAdd(a, row)),
-        (f"{nm} mul a * col[R,1]", (2 * N + R) * s, lambda: c.FillMultiply(a, col)),
+        (f"{nm} add contiguous", 3 * N * s, lambda: c.FillAdd(a, b), k_add),
+        (f"{nm} add a.T + b", 3 * N * s, lambda: c.FillAdd(aT, b), k_addT),
+        (f"{nm} add a + row[1,C]", (2 * N + C) * s, lambda: c.FillAdd(a, row), k_add),
+        (f"{nm} mul a * col[R,1]", (2 * N + R) * s, lambda: c.FillMultiply(a, col), f"ew_kernel<BinaryF<{T_},MUL>> (vector kernel)"),
         (f"{nm} {'sin' if has_sin else 'abs'}(a.T)", 2 * N * s,
-         (lambda: c.FillSin(aT)) if has_sin else (lambda: c.FillAbs(aT))),
-        (f"{nm} add a[1:,1:] + b[1:,1:]", 3 * (R - 1) * (C - 1) * s, lambda: cs.FillAdd(as_, bs)),
-        (f"{nm} add reverseAxis0(a) + b", 3 * N * s, lambda: c.FillAdd(ar0, b)),
-        (f"{nm} add reverseAxis1(a) + b", 3 * N * s, lambda: c.FillAdd(ar1, b)),
-        (f"{nm} copy a.T", 2 * N * s, lambda: c.CopyFrom(aT)),
-        (f"{nm} less a < b.T -> bool", (2 * s + 1) * N, lambda: mask.FillLess(a, b.T)),
-        (f"{nm} ifThenElse(mask, a, b)", (3 * s + 1) * N, lambda: c.FillIfThenElse(mask, a, b)),
+         (lambda: c.FillSin(aT)) if has_sin else (lambda: c.FillAbs(aT)), f"ew_xpose_kernel<UnaryF<{T_}>>"),
+        (f"{nm} add a[1:,1:] + b[1:,1:]", 3 * (R - 1) * (C - 1) * s, lambda: cs.FillAdd(as_, bs), k_add),
+        (f"{nm} add reverseAxis0(a) + b", 3 * N * s, lambda: c.FillAdd(ar0, b), k_add),
+        (f"{nm} add reverseAxis1(a) + b", 3 * N * s, lambda: c.FillAdd(ar1, b), k_add),
+        (f"{nm} copy a.T", 2 * N * s, lambda: c.CopyFrom(aT), f"ew_xpose_kernel<CopyF<{8 * s}-bit>>"),
+        (f"{nm} less a < b.T -> bool", (2 * s + 1) * N, lambda: mask.FillLess(a, b.T), f"ew_xpose_kernel<CompareF<{T_},LESS>>"),
+        (f"{nm} ifThenElse(mask, a, b)", (3 * s + 1) * N, lambda: c.FillIfThenElse(mask, a, b), f"ew_kernel<SelectF<{8 * s}-bit>>"),
     ]
     return cases
 
@@ -171,12 +175,12 @@ def run_cpu_cases(side: int, steps: int, warmup: int):
         mask = Tensor.empty((side, side), dtypes.DN_BOOL, HostTensor.Dev)
         cases = build_cases(Tensor, dt, a, b, c, row, col, mask, has_sin)
         per_dtype.append(cases)
-        total_bytes += sum(nb for _, nb, _ in cases)
+        total_bytes += sum(nb for _, nb, _, _ in cases)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         for cases in per_dtype:
-            for _, _, fn in cases:
+            for _, _, fn, _ in cases:
                 fn()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
@@ -358,12 +362,12 @@ def main():
         a, b, row, col, c = w(ta), w(tb), w(trow), w(tcol), w(tc)
         mask = CudaTensor.usingPtr(tm.data_ptr(), (side, side), dtypes.DN_BOOL, owner=tm)
         per_dtype.append((dt, build_cases(Tensor, dt, a, b, c, row, col, mask, has_sin), (a, b, c)))
-    step_bytes = sum(nb for _, cases, _ in per_dtype for _, nb, _ in cases)
+    step_bytes = sum(nb for _, cases, _ in per_dtype for _, nb, _, _ in cases)
     ncalls = sum(len(cases) for _, cases, _ in per_dtype)
 
     def step():
         for _, cases, _ in per_dtype:
-            for _, _, fn in cases:
+            for _, _, fn, _ in cases:
                 fn()
 
     for _ in range(max(3, args.warmup)):
@@ -392,7 +396,7 @@ def main():
     # per-call timing (CUDA events on the launching stream) for the roofline object; outside the timed region
     per_call = []
     for _, cases, _ in per_dtype:
-        for name, nb, fn in cases:
+        for name, nb, fn, ktag in cases:
             ts = []
             for _ in range(5):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -401,25 +405,40 @@ def main():
                 e.record(stream)
                 e.synchronize()
                 ts.append(s.elapsed_time(e))
-            per_call.append((name, nb, statistics.median(ts)))
+            per_call.append((name, nb, statistics.median(ts), ktag))
     clocks = sampler.stop() if rank == 0 else None
     peak, peak_src = load_peaks()
-    # dominant kernel = the call with the largest share of the step
-    dom = max(per_call, key=lambda x: x[2])
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the same calls
-    # (profiles/r01_*.raw.csv); None for calls that have not been captured
+    # dominant kernel = the kernel TYPE with the largest share of the step (several calls launch the same kernel:
+    # contiguous, row-broadcast, reversed and the body of the sliced case all run the 256-bit vector add kernel)
+    groups = {}
+    for name, nb, ms, ktag in per_call:
+        g = groups.setdefault(ktag, {"bytes": 0, "ms": 0.0, "calls": []})
+        g["bytes"] += nb
+        g["ms"] += ms
+        g["calls"].append(name)
+    total_call_ms = sum(x[2] for x in per_call)
+    dom_tag, dom = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    nlaunch = len(dom["calls"])
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of that kernel on the contiguous case, from the
+    # `ncu --set full` captures under profiles/ (None for kernels that have not been captured)
     ncu_traffic = {
-        "single add contiguous": 2.147553e9 + 1.041274e9,      # profiles/r01b_ew_add_contig256.raw.csv
-        "single add a.T + b": 2.147507e9 + 1.039083e9,         # profiles/r01_ew_xpose_addT.raw.csv
-        "single add a[1:,1:] + b[1:,1:]": 2.152425e9 + 1.035520e9,  # profiles/r01_ew_sliced.raw.csv
-        "double add a.T + b": 4.295036e9 + 2.110988e9,         # profiles/r01_ew_xpose_f64_addT.raw.csv
+        "ew_kernel<BinaryF<float,ADD>,VEC=8> (256-bit vector kernel)": 2.147553e9 + 1.041274e9,   # r01b_ew_add_contig256
+        "ew_kernel<BinaryF<double,ADD>,VEC=4> (256-bit vector kernel)": NCU_F64_ADD_TRAFFIC,       # r01c_ew_add_contig256_f64
+        "ew_xpose_kernel<BinaryF<float,ADD>> (register transpose)": 2.147507e9 + 1.039083e9,      # r01_ew_xpose_addT
+        "ew_xpose_kernel<BinaryF<double,ADD>> (register transpose)": 4.295036e9 + 2.110988e9,     # r01_ew_xpose_f64_addT
     }
     roofline = {
-        "bound": "hbm", "kernel": dom[0], "achieved": dom[1] / dom[2] / 1e6, "peak": peak, "unit": "GB/s",
-        "frac": dom[1] / dom[2] / 1e6 / peak, "traffic": ncu_traffic.get(dom[0]) if side == SIDE else None,
-        "algorithmic_bytes": dom[1], "peak_source": peak_src,
-        "share_of_step": dom[2] / sum(x[2] for x in per_call),
-        "per_call_gbs": {n: round(nb / ms / 1e6, 1) for n, nb, ms in per_call},
+        "bound": "hbm", "kernel": dom_tag, "launches_per_step": nlaunch, "calls": dom["calls"],
+        "achieved": dom["bytes"] / dom["ms"] / 1e6, "peak": peak, "unit": "GB/s",
+        "frac": dom["bytes"] / dom["ms"] / 1e6 / peak,
+        "traffic": ncu_traffic.get(dom_tag) if side == SIDE else None,
+        "traffic_note": "DRAM bytes of one launch on the contiguous case (algorithmic: 3 x 2^28 x element size); "
+                        "achieved = algorithmic bytes of all launches of this kernel in a step / their summed duration",
+        "algorithmic_bytes": dom["bytes"] / nlaunch, "peak_source": peak_src,
+        "share_of_step": dom["ms"] / total_call_ms,
+        "per_call_gbs": {n: round(nb / ms / 1e6, 1) for n, nb, ms, _ in per_call},
+        "per_kernel": {k: {"share_of_step": round(v["ms"] / total_call_ms, 4), "GB/s": round(v["bytes"] / v["ms"] / 1e6, 1),
+                           "launches": len(v["calls"])} for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])},
         "step_frac_of_peak": (step_bytes / (ms_per_step * 1e-3) / 1e9) / peak if world == 1 else value / world / peak,
     }
 
@@ -471,7 +490,7 @@ def main():
             api.call("event_record", ev_up[k])
             dev.SetStream(stream.cuda_stream)
             api.call("stream_wait_event", ev_up[k])
-            for _, _, fn in cases:
+            for _, _, fn, _ in cases:
                 fn()
             api.call("event_record", ev_done[k])
             api.call("event_record", ev_free[k])
@@ -513,32 +532,38 @@ def main():
         TD = {torch.float32: dtypes.DN_F32, torch.int64: dtypes.DN_I64, torch.bool: dtypes.DN_BOOL}
         sh = LeadingAxisSharding(lambda t: CudaTensor.usingPtr(t.data_ptr(), tuple(t.shape), TD[t.dtype], owner=t),
                                  torch.device("cuda", local_rank))
-        R3, C3 = 262144, 1000
-        b3, c3 = slab(R3, rank, world)
-        tl = torch.rand(c3, C3, device="cuda") * 100 - 50
-        lg = CudaTensor.usingPtr(tl.data_ptr(), (c3, C3), dtypes.DN_F32, owner=tl)
+        C3 = 1000
 
-        def c3_step():
-            sh.reduce_axis("ArgMaxLastAxis", lg, 1, R3)
-            sh.reduce_axis("MaxLastAxis", lg, 1, R3)
-        for _ in range(3):
-            c3_step()
-        barrier()
-        s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps3 = 10
-        s3.record(stream)
-        for _ in range(reps3):
-            c3_step()
-        e3.record(stream)
-        barrier()
-        t3 = torch.tensor([s3.elapsed_time(e3) / reps3], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-        ms3 = float(t3.item())
-        nb3 = 2 * R3 * C3 * 4 + R3 * 12
-        sharded = {"workload": f"C3 ArgMaxLastAxis + MaxLastAxis over {R3}x{C3} float32, {world} leading-axis shard(s), "
-                               "outputs all-gathered (NCCL)", "ms": ms3, "GB/s": nb3 / ms3 / 1e6, "scaling": "strong"}
-        del tl, lg
+        def c3_time(R3):
+            b3, c3 = slab(R3, rank, world)
+            tl = torch.rand(c3, C3, device="cuda") * 100 - 50
+            lg = CudaTensor.usingPtr(tl.data_ptr(), (c3, C3), dtypes.DN_F32, owner=tl)
+
+            def c3_step():
+                sh.reduce_axis("ArgMaxLastAxis", lg, 1, R3)
+                sh.reduce_axis("MaxLastAxis", lg, 1, R3)
+            for _ in range(3):
+                c3_step()
+            barrier()
+            s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps3 = 10
+            s3.record(stream)
+            for _ in range(reps3):
+                c3_step()
+            e3.record(stream)
+            barrier()
+            t3 = torch.tensor([s3.elapsed_time(e3) / reps3], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            ms3 = float(t3.item())
+            return ms3, (2 * R3 * C3 * 4 + R3 * 12) / ms3 / 1e6
+
+        ms_s, gbs_s = c3_time(262144)            # strong: the config's tensor split over the ranks
+        ms_w, gbs_w = c3_time(262144 * world)    # weak: one config-sized slab per rank
+        sharded = {"workload": f"C3 ArgMaxLastAxis + MaxLastAxis over [R,{C3}] float32, {world} leading-axis shard(s), "
+                               "outputs all-gathered in place (NCCL)",
+                   "strong": {"rows": 262144, "ms": ms_s, "GB/s": gbs_s},
+                   "weak": {"rows": 262144 * world, "ms": ms_w, "GB/s": gbs_w}}
     except Exception as ex:
         sharded = {"error": repr(ex)}
 
