@@ -43,16 +43,22 @@ struct GSParams {
 };
 
 // Decomposes walked position `f` into the byte offset into the walked tensor and the byte offset into the indexed
-// tensor; returns false if an index is out of range.
+// tensor; returns false if an index is out of range. NDI / NDO: compile-time ranks of the walked / indexed tensor
+// (0 = take them from the parameter block); the common small ranks get loop-free index math.
+template <int NDI, int NDO>
 __device__ __forceinline__ bool gs_addresses(const GSParams &p, uint32_t f, int64_t &it_off, int64_t &other_off) {
-    uint32_t pos[DN_MAX_DIMS];
+    const int nd_it = NDI > 0 ? NDI : p.nd_it;
+    const int nd_other = NDO > 0 ? NDO : p.nd_other;
+    constexpr int kMaxI = NDI > 0 ? NDI : DN_MAX_DIMS;
+    constexpr int kMaxO = NDO > 0 ? NDO : DN_MAX_DIMS;
+    uint32_t pos[kMaxI];
     uint32_t rem = f;
     it_off = 0;
 #pragma unroll
-    for (int k = 0; k < DN_MAX_DIMS; ++k) {
-        if (k >= p.nd_it) break;
+    for (int k = 0; k < kMaxI; ++k) {
+        if (k >= nd_it) break;
         uint32_t q, x;
-        if (k == p.nd_it - 1) { x = rem; q = 0; }
+        if (k == nd_it - 1) { x = rem; q = 0; }
         else { q = p.it_div[k].div(rem); x = rem - q * p.it_shape[k]; }
         pos[k] = x;
         it_off += (int64_t)x * p.it_stride[k];
@@ -61,22 +67,22 @@ __device__ __forceinline__ bool gs_addresses(const GSParams &p, uint32_t f, int6
     other_off = 0;
     bool ok = true;
 #pragma unroll
-    for (int d = 0; d < DN_MAX_DIMS; ++d) {
-        if (d >= p.nd_other) break;
+    for (int d = 0; d < kMaxO; ++d) {
+        if (d >= nd_other) break;
         int64_t ix;
         if (p.idx_ptr[d]) {
             int64_t io = 0;
 #pragma unroll
-            for (int k = 0; k < DN_MAX_DIMS; ++k) {
-                if (k >= p.nd_it) break;
+            for (int k = 0; k < kMaxI; ++k) {
+                if (k >= nd_it) break;
                 io += (int64_t)pos[k] * p.idx_stride[d][k];
             }
             ix = *reinterpret_cast<const int64_t *>(p.idx_ptr[d] + io);
         } else {
             ix = 0;  // None: identity on descriptor dim d (walked dim nd_it-1-d, innermost-first)
 #pragma unroll
-            for (int k = 0; k < DN_MAX_DIMS; ++k)
-                if (k == p.nd_it - 1 - d) ix = pos[k];
+            for (int k = 0; k < kMaxI; ++k)
+                if (k == nd_it - 1 - d) ix = pos[k];
         }
         ok = ok && ix >= 0 && ix < p.other_shape[d];
         other_off += ix * p.other_stride[d];
@@ -84,7 +90,7 @@ __device__ __forceinline__ bool gs_addresses(const GSParams &p, uint32_t f, int6
     return ok;
 }
 
-template <class B>
+template <class B, int NDI, int NDO>
 __global__ void __launch_bounds__(kIdxThreads) gather_kernel(const __grid_constant__ GSParams p) {
     constexpr int U = 4;
     for (uint64_t base = (uint64_t)blockIdx.x * (kIdxThreads * U); base < p.n; base += (uint64_t)gridDim.x * (kIdxThreads * U)) {
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(kIdxThreads) gather_kernel(const __grid_consta
         for (int j = 0; j < U; ++j) {
             const uint64_t f = base + (uint32_t)j * kIdxThreads + threadIdx.x;
             state[j] = 0;
-            if (f < p.n) state[j] = gs_addresses(p, (uint32_t)f, to[j], so[j]) ? 1 : 2;
+            if (f < p.n) state[j] = gs_addresses<NDI, NDO>(p, (uint32_t)f, to[j], so[j]) ? 1 : 2;
         }
 #pragma unroll
         for (int j = 0; j < U; ++j)
@@ -121,10 +127,46 @@ template <class T> __device__ __forceinline__ void atomic_add_any(T *addr, T v) 
     }
 }
 
-template <class TS, class TA>
+// Lanes of a warp that add into the SAME target element are combined first (match.any on the target offset, then a
+// segmented shuffle reduction) and only the group's first lane issues the atomic: index distributions with hot
+// spots no longer serialise on one L2 atomic unit (2^26 adds onto 4096 cells: 20 ms without).
+// Warps without duplicates pay one match + one vote.
+template <class T>
+__device__ __forceinline__ void warp_aggregated_add(char *base, int64_t off, T v, bool active) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long key = active ? (unsigned long long)off : ~(unsigned long long)lane;  // inactive: unique
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (__all_sync(0xffffffffu, (peers & (peers - 1)) == 0)) {  // no two lanes share a target
+        if (active) atomic_add_any(reinterpret_cast<T *>(base + off), v);
+        return;
+    }
+    const int leader = __ffs(peers) - 1;
+    unsigned rest = peers & ~(1u << leader);  // the leader accumulates everybody else's value
+    T sum = v;
+    while (__any_sync(0xffffffffu, rest != 0)) {
+        const int src = rest ? __ffs(rest) - 1 : lane;
+        T o;
+        if constexpr (sizeof(T) == 8) {
+            const unsigned long long bits = __shfl_sync(0xffffffffu, *reinterpret_cast<const unsigned long long *>(&v), src);
+            o = *reinterpret_cast<const T *>(&bits);
+        } else {
+            const unsigned bits = __shfl_sync(0xffffffffu, *reinterpret_cast<const unsigned *>(&v), src);
+            o = *reinterpret_cast<const T *>(&bits);
+        }
+        if (rest) {
+            if constexpr (std::is_integral<T>::value) sum = (T)((UnsignedT<T>)sum + (UnsignedT<T>)o);
+            else sum = sum + o;
+            rest &= rest - 1;
+        }
+    }
+    if (active && lane == leader) atomic_add_any(reinterpret_cast<T *>(base + off), sum);
+}
+
+template <class TS, class TA, int NDI, int NDO>
 __global__ void __launch_bounds__(kIdxThreads) scatter_kernel(const __grid_constant__ GSParams p) {
     using T = TA;
     constexpr int U = 4;
+    // whole warps stay in the loop together (the aggregation uses full-warp votes): the bound is per warp
     for (uint64_t base = (uint64_t)blockIdx.x * (kIdxThreads * U); base < p.n; base += (uint64_t)gridDim.x * (kIdxThreads * U)) {
         int64_t so[U], to[U];
         int state[U];
@@ -133,18 +175,32 @@ __global__ void __launch_bounds__(kIdxThreads) scatter_kernel(const __grid_const
         for (int j = 0; j < U; ++j) {
             const uint64_t f = base + (uint32_t)j * kIdxThreads + threadIdx.x;
             state[j] = 0;
+            to[j] = 0;
+            v[j] = T(0);
             if (f < p.n) {
-                state[j] = gs_addresses(p, (uint32_t)f, so[j], to[j]) ? 1 : 2;
+                state[j] = gs_addresses<NDI, NDO>(p, (uint32_t)f, so[j], to[j]) ? 1 : 2;
                 v[j] = (TA)*reinterpret_cast<const TS *>(p.it_ptr + so[j]);
             }
         }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            if (state[j] == 1) atomic_add_any(reinterpret_cast<T *>(p.other_ptr + to[j]), v[j]);
-            else if (state[j] == 2) atomicExch(p.err, 1);
+            warp_aggregated_add<T>(p.other_ptr, to[j], v[j], state[j] == 1);
+            if (state[j] == 2) atomicExch(p.err, 1);
         }
     }
 }
+
+// Rank dispatch: (walked rank, indexed rank) in {1,2,3}^2 are compiled with loop-free index math.
+#define DN_GS_RANK_DISPATCH(NDI_RT, NDO_RT, ...)                                  \
+    do {                                                                          \
+        const int _ri = (NDI_RT), _ro = (NDO_RT);                                 \
+        if (_ri == 1 && _ro == 1) { constexpr int NDI = 1, NDO = 1; __VA_ARGS__; } \
+        else if (_ri == 2 && _ro == 2) { constexpr int NDI = 2, NDO = 2; __VA_ARGS__; } \
+        else if (_ri == 2 && _ro == 1) { constexpr int NDI = 2, NDO = 1; __VA_ARGS__; } \
+        else if (_ri == 1 && _ro == 2) { constexpr int NDI = 1, NDO = 2; __VA_ARGS__; } \
+        else if (_ri == 3 && _ro == 3) { constexpr int NDI = 3, NDO = 3; __VA_ARGS__; } \
+        else { constexpr int NDI = 0, NDO = 0; __VA_ARGS__; }                     \
+    } while (0)
 
 dn_status gs_fill(GSParams &p, const dn_tensor *walked, const dn_tensor *other, const dn_tensor *const *idxs,
                   const char *what) {
@@ -788,7 +844,9 @@ dn_status dn_gather(const dn_tensor *t, const dn_tensor *const *idxs, int32_t ni
     st = gs_fill(p, t, a, idxs, "Gather");
     if (st != DN_OK) return st;
     const int grid = ew_grid_for(p.n, kIdxThreads * 4);
-    DN_SWITCH_SIZE(dtype_size(t->dtype), { DN_LAUNCH((gather_kernel<B>), grid, kIdxThreads, 0, p); });
+    DN_SWITCH_SIZE(dtype_size(t->dtype), {
+        DN_GS_RANK_DISPATCH(p.nd_it, p.nd_other, DN_LAUNCH((gather_kernel<B, NDI, NDO>), grid, kIdxThreads, 0, p));
+    });
     st = launch_status("gather kernel");
     if (st != DN_OK) return st;
     return check_index_error("Gather");
@@ -825,16 +883,16 @@ dn_status dn_scatter(const dn_tensor *t, const dn_tensor *const *idxs, int32_t n
         if (st == DN_OK) {
             const int grid = ew_grid_for(p.n, kIdxThreads * 4);
             switch (t->dtype) {
-            case DN_F32: DN_LAUNCH((scatter_kernel<float, float>), grid, kIdxThreads, 0, p); break;
-            case DN_F64: DN_LAUNCH((scatter_kernel<double, double>), grid, kIdxThreads, 0, p); break;
-            case DN_I8: DN_LAUNCH((scatter_kernel<int8_t, int32_t>), grid, kIdxThreads, 0, p); break;
-            case DN_U8: DN_LAUNCH((scatter_kernel<uint8_t, int32_t>), grid, kIdxThreads, 0, p); break;
-            case DN_I16: DN_LAUNCH((scatter_kernel<int16_t, int32_t>), grid, kIdxThreads, 0, p); break;
-            case DN_U16: DN_LAUNCH((scatter_kernel<uint16_t, int32_t>), grid, kIdxThreads, 0, p); break;
-            case DN_I32: DN_LAUNCH((scatter_kernel<int32_t, int32_t>), grid, kIdxThreads, 0, p); break;
-            case DN_U32: DN_LAUNCH((scatter_kernel<uint32_t, uint32_t>), grid, kIdxThreads, 0, p); break;
-            case DN_I64: DN_LAUNCH((scatter_kernel<int64_t, int64_t>), grid, kIdxThreads, 0, p); break;
-            case DN_U64: DN_LAUNCH((scatter_kernel<uint64_t, uint64_t>), grid, kIdxThreads, 0, p); break;
+            case DN_F32: DN_GS_RANK_DISPATCH(p.nd_it, p.nd_other, DN_LAUNCH((scatter_kernel<float, float, NDI, NDO>), grid, kIdxThreads, 0, p)); break;
+            case DN_F64: DN_GS_RANK_DISPATCH(p.nd_it, p.nd_other, DN_LAUNCH((scatter_kernel<double, double, NDI, NDO>), grid, kIdxThreads, 0, p)); break;
+            case DN_I8: DN_GS_RANK_DISPATCH(p.nd_it, p.nd_other, DN_LAUNCH((scatter_kernel<int8_t, int32_t, NDI, NDO>), grid, kIdxThreads, 0, p)); break;
+            case DN_U8: DN_GS_RANK_DISPATCH(p.nd_it, p.nd_other, DN_LAUNCH((scatter_kernel<uint8_t, int32_t, NDI, NDO>), grid, kIdxThreads, 0, p)); break;
+            case DN_I16: DN_GS_RANK_DISPATCH(p.nd_it, p.nd_other, DN_LAUNCH((scatter_kernel<int16_t, int32_t, NDI, NDO>), grid, kIdxThreads, 0, p)); break;
+            case DN_U16: DN_GS_RANK_DISPATCH(p.nd_it, p.nd_other, DN_LAUNCH((scatter_kernel<uint16_t, int32_t, NDI, NDO>), grid, kIdxThreads, 0, p)); break;
+            case DN_I32: DN_GS_RANK_DISPATCH(p.nd_it, p.nd_other, DN_LAUNCH((scatter_kernel<int32_t, int32_t, NDI, NDO>), grid, kIdxThreads, 0, p)); break;
+            case DN_U32: DN_GS_RANK_DISPATCH(p.nd_it, p.nd_other, DN_LAUNCH((scatter_kernel<uint32_t, uint32_t, NDI, NDO>), grid, kIdxThreads, 0, p)); break;
+            case DN_I64: DN_GS_RANK_DISPATCH(p.nd_it, p.nd_other, DN_LAUNCH((scatter_kernel<int64_t, int64_t, NDI, NDO>), grid, kIdxThreads, 0, p)); break;
+            case DN_U64: DN_GS_RANK_DISPATCH(p.nd_it, p.nd_other, DN_LAUNCH((scatter_kernel<uint64_t, uint64_t, NDI, NDO>), grid, kIdxThreads, 0, p)); break;
             default: st = set_error(DN_ERR_INVALID_ARG, "bad dtype"); break;
             }
             if (st == DN_OK) st = launch_status("scatter kernel");

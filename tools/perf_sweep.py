@@ -143,6 +143,25 @@ def main():
     run("C4 i64 gather permutation 2^26", 3 * 8 * N, lambda: trg.FillGather([perm], src))
     run("C4 i64 scatter random 2^26", (8 + 8 + 8 + 16) * N, lambda: trg.FillScatter([idx], src))
     run("C4 i64 scatter permutation 2^26", (8 + 8 + 8 + 16) * N, lambda: trg.FillScatter([perm], src))
+    # C4 variants: hot-spot indices (collisions), 2-D row gather [Some i0; None], sparse masks
+    thot = (torch.rand(N, device="cuda") ** 8 * 4096).to(torch.int64)          # most indices fall on a few cells
+    hot = wrap(thot)
+    run("C4 i64 scatter hot-spot (4096 cells) 2^26", (8 + 8 + 16) * N, lambda: trg.FillScatter([hot], src))
+    run("C4 i64 gather hot-spot 2^26", 3 * 8 * N, lambda: trg.FillGather([hot], src))
+    tsrc2 = tsrc.view(8192, 8192)
+    src2 = wrap(tsrc2)
+    trow = torch.randint(0, 8192, (8192, 1), device="cuda", dtype=torch.int64)
+    rowidx = wrap(trow).broadcastTo((8192, 8192))
+    trg2 = Tensor.empty((8192, 8192), dtypes.DN_I64, dev)
+    run("C4 i64 gather rows [Some i0; None] 8192^2", 2 * 8 * N + 8 * 8192, lambda: trg2.FillGather([rowidx, None], src2))
+    tms = torch.rand(N, device="cuda") < 0.01
+    msp = wrap(tms)
+    nsp = int(tms.sum().item())
+    gsp = Tensor.empty((nsp,), dtypes.DN_I64, dev)
+    run("C4 i64 maskedGet p=0.01 2^26", N + 8 * N + 8 * nsp, lambda: src.Backend.MaskedGet(gsp, src, [msp]))
+    run("C4 i64 maskedSet p=0.01 2^26", N + 16 * nsp, lambda: trg.Backend.MaskedSet(trg, [msp], gsp))
+    tisp = Tensor.empty((nsp, 2), dtypes.DN_I64, dev)
+    run("C4 trueIdx [8192,8192] p=0.01", N + 16 * nsp, lambda: tisp.Backend.TrueIndices(tisp, msp.reshape((8192, 8192))))
     tmask = torch.rand(N, device="cuda") < 0.5
     mask = wrap(tmask)
     ntrue = int(tmask.sum().item())
