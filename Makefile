@@ -37,7 +37,10 @@ $(LIB): $(OBJECTS)
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HEADERS)
 	@mkdir -p $(OBJ)
-	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+	$(NVCC) $(NVCCFLAGS) $(EXTRA_$*) -c $< -o $@
+
+# the fused-expression interpreter must round every instruction like the single operator it stands for
+EXTRA_ew_fused := -fmad=false
 
 # one generated translation unit per conversion target type
 build/gen/ew_convert_%.cu: $(SRC)/ew_convert.cu.in

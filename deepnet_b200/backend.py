@@ -171,6 +171,14 @@ class NativeTensorBackend:
     def BatchedMatMatDot(self, trgt, src1, src2) -> None:
         self._call("batched_mat_mat_dot", self._d(trgt), self._d(src1), self._d(src2))
 
+    def FusedElemwise(self, trgt, srcs: List[object], prog: List[tuple]) -> None:
+        """dn_fused_elemwise (new): `prog` = [(kind, op, dst, a, b, imm)], see include/dn_tensor.h."""
+        arr = (native.dn_fused_instr * len(prog))()
+        for i, (kind, op, dst, a, b, imm) in enumerate(prog):
+            arr[i] = native.dn_fused_instr(kind, op, dst, a, b, float(imm))
+        descs = [self._d(x) for x in srcs]
+        self._call("fused_elemwise", self._d(trgt), native.desc_ptr_array(descs), len(descs), arr, len(prog))
+
     def BatchedInvert(self, trgt, src) -> None:
         """TensorBackend.fs:142; CudaBackend.fs:451-484. Raises SingularMatrixException."""
         self._call("batched_invert", self._d(trgt), self._d(src))

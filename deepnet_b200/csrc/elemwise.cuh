@@ -210,6 +210,11 @@ struct EwSig {
     // Packed functors (1-byte bool operators) also provide `uint32_t packed(uint32_t...)` over four elements per
     // 32-bit word; the vector kernel uses it instead of sixteen byte-wide evaluations per 128-bit access.
     static constexpr bool Packed = false;
+    // VectorEval functors evaluate a whole work item at once: `eval(Out (&r)[VEC], const In0 (&a)[VEC], ...)`
+    // (the fused-expression interpreter amortises its instruction decode over the VEC elements).
+    static constexpr bool VectorEval = false;
+    static constexpr int MaxInFlight = 8;  // cap on U, the work items a thread keeps in flight
+    static constexpr int MinBlocks = 1;    // __launch_bounds__ minimum resident CTAs per SM
 };
 
 template <int NOPS, int ND>
@@ -248,7 +253,7 @@ __device__ __forceinline__ void ew_offsets(const EwParams<NOPS> &p, uint32_t idx
 
 // F: struct : EwSig<...> { __device__ Out operator()(In...) const; }
 template <class F, int VEC, int U, int ND>
-__global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ EwParams<F::NSRC + 1> p, const F f) {
+__global__ void __launch_bounds__(kEwThreads, F::MinBlocks) ew_kernel(const __grid_constant__ EwParams<F::NSRC + 1> p, const __grid_constant__ F f) {
     constexpr int NOPS = F::NSRC + 1;
     using Out = typename F::Out;
     using P0 = InPack<typename F::In0, VEC>;
@@ -279,7 +284,11 @@ __global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ 
             const uint64_t idx = base + (uint32_t)j * kEwThreads + threadIdx.x;
             if (idx < p.n) {
                 Pack<Out, VEC> r;
-                if constexpr (F::Packed && VEC % 4 == 0) {
+                if constexpr (F::VectorEval) {
+                    if constexpr (F::NSRC == 1) f.template eval<VEC>(r.v, a[j].p.v, a[j].p.v, a[j].p.v);
+                    else if constexpr (F::NSRC == 2) f.template eval<VEC>(r.v, a[j].p.v, b[j].p.v, b[j].p.v);
+                    else f.template eval<VEC>(r.v, a[j].p.v, b[j].p.v, c[j].p.v);
+                } else if constexpr (F::Packed && VEC % 4 == 0) {
                     uint32_t *wr = reinterpret_cast<uint32_t *>(&r);
 #pragma unroll
                     for (int e = 0; e < VEC / 4; ++e) {
@@ -573,7 +582,8 @@ template <class F, int VEC>
 dn_status ew_launch_strided(const EwPlan &plan, const F &f, int64_t n_inner0_elems) {
     constexpr int NOPS = F::NSRC + 1;
     // U: independent work items per thread; 64-128 bytes of loads per source in flight per thread
-    constexpr int U = VEC == 1 ? (F::MaxSize >= 8 ? 4 : 8) : ((VEC * F::MaxSize >= 64) ? 1 : ((VEC * F::MaxSize >= 32) ? 2 : 4));
+    constexpr int U0 = VEC == 1 ? (F::MaxSize >= 8 ? 4 : 8) : ((VEC * F::MaxSize >= 64) ? 1 : ((VEC * F::MaxSize >= 32) ? 2 : 4));
+    constexpr int U = U0 < F::MaxInFlight ? U0 : F::MaxInFlight;
     EwPlan local = plan;
     local.shape[0] = n_inner0_elems;
     const int nd = local.ndims;

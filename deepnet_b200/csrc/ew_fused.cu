@@ -1,0 +1,184 @@
+// ew_fused.cu — dn_fused_elemwise: a straight-line element-wise program evaluated in ONE pass over the operands
+// (SURVEY.md §8f-3). The reference has no such backend member: it fuses only through the Symbolic layer's
+// NVRTC-generated "elements" kernels; its Tensor API runs `a*b + sin a` as three kernels and 512 MiB of traffic
+// instead of 192 MiB (Tensor.Benchmark/Benchmark.fs).
+//
+// No run-time compilation: the program is interpreted, but per WORK ITEM (16 bytes), not per element. The six
+// virtual registers are 16-byte slots in shared memory, private to the thread, so operand fetch and write-back are
+// one 128-bit shared-memory access each and decoding costs a handful of instructions per element and program
+// instruction — below the ~66 instructions per element an HBM-bound f32 kernel with three streams can afford. Every instruction rounds to the element type like the single operator it stands for; this
+// translation unit is compiled with -fmad=false so that no multiply-add is contracted and the result equals the
+// unfused call sequence bit for bit.
+#include "ew_ops.cuh"
+
+using namespace dn;
+
+namespace {
+
+struct FusedInstr {
+    uint8_t kind, op, dst, a, b;
+};
+
+template <class T, int NS>
+struct FusedSig;
+template <class T> struct FusedSig<T, 1> { using type = EwSig<T, T>; };
+template <class T> struct FusedSig<T, 2> { using type = EwSig<T, T, T>; };
+template <class T> struct FusedSig<T, 3> { using type = EwSig<T, T, T, T>; };
+
+template <class T, int NS>
+struct FusedF : FusedSig<T, NS>::type {
+    static constexpr bool VectorEval = true;
+    static constexpr bool Tiled = false;  // transposed operands take the strided kernel (VEC = 1)
+    // 16-byte work items = one register-file slot; consecutive lanes still write consecutive 16-byte pieces,
+    // i.e. whole sectors per warp-level store
+    static constexpr int Vec = 16 / (int)sizeof(T);
+    static constexpr int MaxInFlight = 4;
+    static constexpr int MinBlocks = 4;    // 24 KiB of register-file slots per CTA
+    int32_t n;
+    FusedInstr ins[DN_FUSED_MAX_INSTRS];
+    T imm[DN_FUSED_MAX_INSTRS];
+
+    template <int OP, int VEC>
+    __device__ __forceinline__ static void unary_all(T (&z)[VEC], const T (&x)[VEC]) {
+        UnaryF<T, OP> f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) z[e] = f(x[e]);
+    }
+    template <int OP, int VEC>
+    __device__ __forceinline__ static void binary_all(T (&z)[VEC], const T (&x)[VEC], const T (&y)[VEC]) {
+        BinaryF<T, OP> f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) z[e] = f(x[e], y[e]);
+    }
+
+    // The virtual register file lives in shared memory, one 16-byte slot per (register, thread): operand fetch and
+    // write-back are ONE 128-bit shared-memory access each whatever the register number (keeping the file in
+    // hardware registers makes the compiler if-convert the register switches into ~25 predicated moves per
+    // element and instruction — measured 36 % of the HBM rate). Slots are thread-private: no barriers.
+    static constexpr int kSlotElems = 16 / (int)sizeof(T);
+    struct alignas(16) Slot { T v[kSlotElems]; };
+
+    template <int VEC>
+    __device__ __forceinline__ void eval(T (&out)[VEC], const T (&s0)[VEC], const T (&s1)[VEC], const T (&s2)[VEC]) const {
+        static_assert(VEC <= kSlotElems, "work items are at most 16 bytes");
+        __shared__ Slot rf[DN_FUSED_REGS][kEwThreads];
+        const int tid = threadIdx.x;
+        auto put = [&](int reg, const T (&v)[VEC]) {
+            Slot sl;
+#pragma unroll
+            for (int e = 0; e < kSlotElems; ++e) sl.v[e] = e < VEC ? v[e] : T(0);
+            rf[reg][tid] = sl;
+        };
+        auto get = [&](int reg, T (&v)[VEC]) {
+            const Slot sl = rf[reg][tid];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[e] = sl.v[e];
+        };
+        put(0, s0);
+        if (NS > 1) put(1, s1);
+        if (NS > 2) put(2, s2);
+        T z[VEC];
+#pragma unroll 1
+        for (int k = 0; k < n; ++k) {
+            const FusedInstr in = ins[k];
+            T x[VEC], y[VEC];
+            if (in.kind == DN_FUSED_CONST) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) z[e] = imm[k];
+            } else {
+                get(in.a, x);
+                if (in.kind == DN_FUSED_UNARY) {
+                    switch (in.op) {
+#define DN_U(OP) case OP: unary_all<OP, VEC>(z, x); break;
+                        DN_U(DN_UNARY_MINUS) DN_U(DN_ABS) DN_U(DN_SGN) DN_U(DN_LOG) DN_U(DN_LOG10) DN_U(DN_EXP) DN_U(DN_SIN)
+                        DN_U(DN_COS) DN_U(DN_TAN) DN_U(DN_ASIN) DN_U(DN_ACOS) DN_U(DN_ATAN) DN_U(DN_SINH) DN_U(DN_COSH)
+                        DN_U(DN_TANH) DN_U(DN_SQRT) DN_U(DN_CEILING) DN_U(DN_FLOOR) DN_U(DN_ROUND) DN_U(DN_TRUNCATE)
+#undef DN_U
+                    default:  // UnaryPlus
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) z[e] = x[e];
+                    }
+                } else {
+                    get(in.b, y);
+                    switch (in.op) {
+#define DN_B(OP) case OP: binary_all<OP, VEC>(z, x, y); break;
+                        DN_B(DN_SUBTRACT) DN_B(DN_MULTIPLY) DN_B(DN_DIVIDE) DN_B(DN_MODULO) DN_B(DN_POWER)
+                        DN_B(DN_MAX_ELEMWISE) DN_B(DN_MIN_ELEMWISE)
+#undef DN_B
+                    default: binary_all<DN_ADD, VEC>(z, x, y);
+                    }
+                }
+            }
+            put(in.dst, z);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) out[e] = z[e];  // the last instruction's value
+    }
+
+    // element-at-a-time form (not used by the kernels this functor is instantiated for, required by the interface)
+    __device__ __forceinline__ T operator()(T a) const { T o[1], x[1] = {a}; eval<1>(o, x, x, x); return o[0]; }
+    __device__ __forceinline__ T operator()(T a, T b) const { T o[1], x[1] = {a}, y[1] = {b}; eval<1>(o, x, y, y); return o[0]; }
+    __device__ __forceinline__ T operator()(T a, T b, T c) const {
+        T o[1], x[1] = {a}, y[1] = {b}, w[1] = {c};
+        eval<1>(o, x, y, w);
+        return o[0];
+    }
+};
+
+template <class T, int NS>
+dn_status run_fused(EwPlan &plan, const dn_fused_instr *prog, int n) {
+    FusedF<T, NS> f;
+    f.n = n;
+    for (int k = 0; k < DN_FUSED_MAX_INSTRS; ++k) {
+        f.ins[k] = FusedInstr{0, 0, 0, 0, 0};
+        f.imm[k] = T(0);
+        if (k < n) {
+            f.ins[k] = FusedInstr{(uint8_t)prog[k].kind, (uint8_t)prog[k].op, (uint8_t)prog[k].dst, (uint8_t)prog[k].a, (uint8_t)prog[k].b};
+            f.imm[k] = (T)prog[k].imm;
+        }
+    }
+    return ew_run(plan, f);
+}
+
+}  // namespace
+
+extern "C" dn_status dn_fused_elemwise(const dn_tensor *t, const dn_tensor *const *srcs, int32_t nsrc, const dn_fused_instr *prog,
+                                       int32_t ninstr) {
+    if (!tensor_valid(t) || !srcs || !prog) return set_error(DN_ERR_INVALID_ARG, "FusedElemwise: bad argument");
+    if (nsrc < 1 || nsrc > DN_FUSED_MAX_SRCS) return set_error(DN_ERR_INVALID_ARG, "FusedElemwise: 1 to %d sources are supported", DN_FUSED_MAX_SRCS);
+    if (ninstr < 1 || ninstr > DN_FUSED_MAX_INSTRS)
+        return set_error(DN_ERR_INVALID_ARG, "FusedElemwise: 1 to %d instructions are supported", DN_FUSED_MAX_INSTRS);
+    if (t->dtype != DN_F32 && t->dtype != DN_F64) return set_error(DN_ERR_UNSUPPORTED, "FusedElemwise is only supported for single and double");
+    for (int k = 0; k < nsrc; ++k)
+        if (!tensor_valid(srcs[k]) || srcs[k]->dtype != t->dtype) return set_error(DN_ERR_INVALID_ARG, "FusedElemwise: operand types differ");
+    // a register must be written (a source, or the destination of an earlier instruction) before it is read
+    uint32_t written = (1u << nsrc) - 1;
+    for (int k = 0; k < ninstr; ++k) {
+        const dn_fused_instr &in = prog[k];
+        if (in.dst < 0 || in.dst >= DN_FUSED_REGS) return set_error(DN_ERR_INVALID_ARG, "FusedElemwise: instruction %d: bad destination register", k);
+        if (in.kind == DN_FUSED_UNARY) {
+            if (in.op < 0 || in.op > DN_TRUNCATE) return set_error(DN_ERR_UNSUPPORTED, "FusedElemwise: instruction %d: unary op %d", k, in.op);
+        } else if (in.kind == DN_FUSED_BINARY) {
+            if (in.op < 0 || in.op > DN_MIN_ELEMWISE) return set_error(DN_ERR_UNSUPPORTED, "FusedElemwise: instruction %d: binary op %d", k, in.op);
+        } else if (in.kind != DN_FUSED_CONST) {
+            return set_error(DN_ERR_INVALID_ARG, "FusedElemwise: instruction %d: bad kind", k);
+        }
+        const int nread = in.kind == DN_FUSED_CONST ? 0 : (in.kind == DN_FUSED_UNARY ? 1 : 2);
+        const int regs[2] = {in.a, in.b};
+        for (int q = 0; q < nread; ++q)
+            if (regs[q] < 0 || regs[q] >= DN_FUSED_REGS || !((written >> regs[q]) & 1u))
+                return set_error(DN_ERR_INVALID_ARG, "FusedElemwise: instruction %d reads register %d before it is written", k, regs[q]);
+        written |= 1u << in.dst;
+    }
+    EwPlan plan;
+    dn_status st = ew_make_plan(plan, t, srcs, nsrc);
+    if (st != DN_OK) return st;
+    if (t->dtype == DN_F32) {
+        if (nsrc == 1) return run_fused<float, 1>(plan, prog, ninstr);
+        if (nsrc == 2) return run_fused<float, 2>(plan, prog, ninstr);
+        return run_fused<float, 3>(plan, prog, ninstr);
+    }
+    if (nsrc == 1) return run_fused<double, 1>(plan, prog, ninstr);
+    if (nsrc == 2) return run_fused<double, 2>(plan, prog, ninstr);
+    return run_fused<double, 3>(plan, prog, ninstr);
+}

@@ -61,6 +61,16 @@ class dn_tensor(C.Structure):
     ]
 
 
+class dn_fused_instr(C.Structure):
+    """include/dn_tensor.h `dn_fused_instr`."""
+    _fields_ = [("kind", C.c_int32), ("op", C.c_int32), ("dst", C.c_int32), ("a", C.c_int32), ("b", C.c_int32),
+                ("imm", C.c_double)]
+
+
+DN_FUSED_UNARY, DN_FUSED_BINARY, DN_FUSED_CONST = range(3)
+DN_FUSED_REGS, DN_FUSED_MAX_INSTRS, DN_FUSED_MAX_SRCS = 6, 12, 3
+
+
 def make_desc(base: int, layout: TensorLayout, dtype: int) -> dn_tensor:
     if layout.NDims > DN_MAX_DIMS:
         raise NotSupportedException(f"tensors of rank {layout.NDims} > {DN_MAX_DIMS} are not supported")
@@ -103,6 +113,7 @@ _OPERATOR_SIGNATURES = {
     "mat_mat_dot": [_P, _P, _P],
     "batched_mat_mat_dot": [_P, _P, _P],
     "batched_invert": [_P, _P],
+    "fused_elemwise": [_P, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32],
 }
 
 # device / storage entry points exported only by the product library

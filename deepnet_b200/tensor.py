@@ -522,6 +522,23 @@ class Tensor:
             raise ValueError(f"Cannot compute dot product between tensors of shapes {a.Shape} and {b.Shape} "
                              f"into tensor of shape {self.Shape}.")
 
+    # ---- fused element-wise expressions (new) ------------------------------------------------
+    def FillFused(self, fn, *srcs: "Tensor") -> None:
+        """Evaluates `fn(*srcs)` — an expression of +, -, *, /, %, **, unary minus, abs and the unary functions
+        (sin, exp, tanh, ...) over up to three tensors and Python scalars — in ONE backend call
+        (ITensorBackend extension `FusedElemwise`), with the rounding of the operator-by-operator evaluation."""
+        from .fused import trace
+        srcs = Tensor.PrepareElemwiseSources(self, *srcs)
+        prog = trace(fn, len(srcs))
+        self.Backend.FusedElemwise(self, list(srcs), prog)
+
+    @staticmethod
+    def fused(fn, *srcs: "Tensor") -> "Tensor":
+        trgt, *bsrcs = Tensor.PrepareElemwise(srcs[0].DataType, *srcs)
+        from .fused import trace
+        trgt.Backend.FusedElemwise(trgt, list(bsrcs), trace(fn, len(bsrcs)))
+        return trgt
+
     def FillInvert(self, a: "Tensor") -> None:
         """Tensor.FillInvert, Tensor.fs:2809-2815."""
         Tensor.CheckSameStorage(self, a)

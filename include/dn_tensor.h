@@ -169,6 +169,28 @@ dn_status dn_is_finite(const dn_tensor *t, const dn_tensor *a);
 dn_status dn_if_then_else(const dn_tensor *t, const dn_tensor *cond, const dn_tensor *if_true,
                           const dn_tensor *if_false);
 
+/* Fused element-wise expression (new; SURVEY.md §8f-3 — the reference reaches fusion only through the Symbolic
+ * layer's generated "elements" kernels, Examples/LearnMnist/Program.fs:14). One pass over the operands evaluates a
+ * short straight-line program over six virtual registers: the sources are preloaded into registers 0..nsrc-1, every
+ * instruction computes r[dst] = op(r[a] [, r[b]]) or r[dst] = imm, the target receives r[dst of the last
+ * instruction]. Each instruction rounds to the element type exactly like the corresponding single operator
+ * (no fused multiply-add), so the result is bit-identical to the sequence of dn_unary / dn_binary calls it replaces
+ * while moving (nsrc + 1) instead of ~3 tensors per operator through HBM. f32 / f64; all operands of one type.
+ * Example, c = a*b + sin(a):  {BINARY MULTIPLY 2 <- 0,1} {UNARY SIN 3 <- 0} {BINARY ADD 2 <- 2,3}. */
+typedef enum dn_fused_kind { DN_FUSED_UNARY = 0, DN_FUSED_BINARY = 1, DN_FUSED_CONST = 2 } dn_fused_kind;
+typedef struct dn_fused_instr {
+    int32_t kind;   /* dn_fused_kind                                                            */
+    int32_t op;     /* dn_unary_op (UNARY) / dn_binary_op Add..MinElemwise (BINARY) / unused    */
+    int32_t dst;    /* 0..DN_FUSED_REGS-1                                                       */
+    int32_t a, b;   /* operand registers; b is ignored by UNARY, both by CONST                  */
+    double  imm;    /* CONST: the value, converted to the element type                          */
+} dn_fused_instr;
+#define DN_FUSED_REGS 6
+#define DN_FUSED_MAX_INSTRS 12
+#define DN_FUSED_MAX_SRCS 3
+dn_status dn_fused_elemwise(const dn_tensor *t, const dn_tensor *const *srcs, int32_t nsrc,
+                            const dn_fused_instr *prog, int32_t ninstr);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Last-axis reductions.  a has shape [..., L], t has shape [...].
  * ------------------------------------------------------------------------------------------------------------- */

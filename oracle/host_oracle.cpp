@@ -1195,3 +1195,52 @@ dn_status dno_batched_invert(const dn_tensor *t, const dn_tensor *a) {
 }
 
 }  // extern "C"
+
+// Fused element-wise expression (dn_fused_elemwise, include/dn_tensor.h): the reference has no such member — the
+// oracle defines it as EXACTLY the sequence of host operators it stands for: every instruction is unary_eval /
+// binary_eval of the element type (ScalarOps.fs:381-533 semantics, intermediate results rounded to T).
+extern "C" dn_status dno_fused_elemwise(const dn_tensor *t, const dn_tensor *const *srcs, int32_t nsrc,
+                                        const dn_fused_instr *prog, int32_t ninstr) {
+    if (!valid(t) || !srcs || !prog || nsrc < 1 || nsrc > DN_FUSED_MAX_SRCS || ninstr < 1 || ninstr > DN_FUSED_MAX_INSTRS)
+        return fail(DN_ERR_INVALID_ARG, "fused_elemwise: bad argument");
+    if (t->dtype != DN_F32 && t->dtype != DN_F64) return fail(DN_ERR_UNSUPPORTED, "fused_elemwise: f32/f64 only");
+    for (int k = 0; k < nsrc; ++k) {
+        if (!valid(srcs[k]) || srcs[k]->dtype != t->dtype) return fail(DN_ERR_INVALID_ARG, "fused_elemwise: dtype mismatch");
+        if (!same_shape(t, srcs[k])) return fail(DN_ERR_SHAPE_MISMATCH, "fused_elemwise: shape mismatch");
+    }
+    uint32_t written = (1u << nsrc) - 1;
+    for (int k = 0; k < ninstr; ++k) {
+        const dn_fused_instr &in = prog[k];
+        if (in.dst < 0 || in.dst >= DN_FUSED_REGS) return fail(DN_ERR_INVALID_ARG, "fused_elemwise: bad destination");
+        const int nread = in.kind == DN_FUSED_CONST ? 0 : (in.kind == DN_FUSED_UNARY ? 1 : 2);
+        if (in.kind == DN_FUSED_UNARY && (in.op < 0 || in.op > DN_TRUNCATE)) return fail(DN_ERR_UNSUPPORTED, "fused_elemwise: unary op");
+        if (in.kind == DN_FUSED_BINARY && (in.op < 0 || in.op > DN_MIN_ELEMWISE)) return fail(DN_ERR_UNSUPPORTED, "fused_elemwise: binary op");
+        if (in.kind < 0 || in.kind > DN_FUSED_CONST) return fail(DN_ERR_INVALID_ARG, "fused_elemwise: bad kind");
+        const int regs[2] = {in.a, in.b};
+        for (int q = 0; q < nread; ++q)
+            if (regs[q] < 0 || regs[q] >= DN_FUSED_REGS || !((written >> regs[q]) & 1u))
+                return fail(DN_ERR_INVALID_ARG, "fused_elemwise: register read before written");
+        written |= 1u << in.dst;
+    }
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        Operand ops[4] = {operand_of<T>(t), operand_of<T>(srcs[0]), operand_of<T>(srcs[nsrc > 1 ? 1 : 0]),
+                          operand_of<T>(srcs[nsrc > 2 ? 2 : 0])};
+        elemwise_drive<4>(t->ndims, t->shape, ops, false, true, [&](char **p) {
+            T r[DN_FUSED_REGS] = {};
+            for (int k = 0; k < nsrc; ++k) r[k] = *(const T *)p[1 + k];
+            T z = T(0);
+            for (int k = 0; k < ninstr; ++k) {
+                const dn_fused_instr &in = prog[k];
+                if (in.kind == DN_FUSED_CONST) z = (T)in.imm;
+                else if (in.kind == DN_FUSED_UNARY) z = unary_eval<T>(in.op, r[in.a]);
+                else z = binary_eval<T>(in.op, r[in.a], r[in.b]);
+                r[in.dst] = z;
+            }
+            *(T *)p[0] = z;
+        });
+    };
+    if (t->dtype == DN_F32) run(0.0f);
+    else run(0.0);
+    return DN_OK;
+}

@@ -120,6 +120,21 @@ def main():
     run("C1 f32 sin 4096^2", 2 * n1, lambda: t2.FillSin(a))
     run("C1 f32 add 4096^2", 3 * n1, lambda: c.FillAdd(t1, t2))
     run("C1 f32 sumAxis1 4096^2", n1 + 4096 * 4, lambda: out.FillSumAxis(1, c))
+    run("C1 f32 FUSED a*b+sin(a) 4096^2 (one call)", 3 * n1, lambda: c.FillFused(lambda x, y: x * y + x.sin(), a, b))
+    # fused expressions at 2^28 elements
+    tfa, tfb = rand((R, Cc), dtypes.DN_F32), rand((R, Cc), dtypes.DN_F32)
+    fa, fb = wrap(tfa), wrap(tfb)
+    fc = wrap(torch.empty((R, Cc), device="cuda", dtype=torch.float32))
+    nf = R * Cc * 4
+    run("FUSED f32 a*b+sin(a) 2^28", 3 * nf, lambda: fc.FillFused(lambda x, y: x * y + x.sin(), fa, fb))
+    run("FUSED f32 dh*(1-h*h) 2^28", 3 * nf, lambda: fc.FillFused(lambda x, y: x * (1.0 - y * y), fa, fb))
+    run("FUSED f32 w-g*0.01 in place 2^28", 3 * nf, lambda: fa.FillFused(lambda x, y: x - y * 0.01, fa, fb))
+    run("FUSED f32 (a-b)*c/(|c|+2.5) 2^28", 4 * nf, lambda: fc.FillFused(lambda x, y, z: (x - y) * z / (abs(z) + 2.5), fa, fb, fc))
+    tda, tdb = rand((R, Cc), dtypes.DN_F64), rand((R, Cc), dtypes.DN_F64)
+    da, db = wrap(tda), wrap(tdb)
+    dcc = wrap(torch.empty((R, Cc), device="cuda", dtype=torch.float64))
+    run("FUSED f64 dh*(1-h*h) 2^28", 3 * nf * 2, lambda: dcc.FillFused(lambda x, y: x * (1.0 - y * y), da, db))
+    del tfa, tfb, fa, fb, fc, tda, tdb, da, db, dcc
 
     # C3
     tl = rand((262144, 1000), dtypes.DN_F32)
