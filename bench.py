@@ -229,6 +229,14 @@ def measure_other_configs(dev, torch, peak):
         c.FillAdd(t1, t2)
         o1.FillSumAxis(1, c)
     hbm("C1 a*b+sin(a) (3 calls) + SumLastAxis 4096x4096 [small kernels: includes host launch gaps]", 9 * n1 + 4096 * 4, c1, 8)
+    from deepnet_b200.fused import trace
+    prog_c1 = trace(lambda x, y: x * y + x.sin(), 2)
+
+    def c1_fused():
+        c.Backend.FusedElemwise(c, [a, b], prog_c1)
+        o1.FillSumAxis(1, c)
+    hbm("C1 FUSED a*b+sin(a) (1 call, dn_fused_elemwise) + SumLastAxis 4096x4096 [bytes of the fused form]",
+        4 * n1 + 4096 * 4, c1_fused, 8)
     td = torch.rand(8192, 8192, device="cuda", dtype=torch.float64) * 100 - 50
     dd, dc = w(td, dtypes.DN_F64), Tensor.empty((8192, 8192), dtypes.DN_F64, dev)
     hbm("float64 sin 8192x8192 (FP64-compute-bound on B200, not an HBM kernel)", 2 * 8 * 8192 * 8192, lambda: dc.FillSin(dd))
@@ -272,6 +280,9 @@ def measure_other_configs(dev, torch, peak):
     fl = flops_per_step(batch, sizes)
     out["C5 MLP 784-4096-4096-10 batch 8192 training step"] = {"ms": round(ms, 3), "TFLOP/s": round(fl / ms / 1e9, 1),
                                                               "gemm_tflop_per_step": round(fl / 1e12, 3)}
+    ms_f = timed(lambda: train_step(x, t, params, 1e-3, fused=True), 3)
+    out["C5 MLP training step with FusedElemwise (same bits, fewer passes over HBM)"] = {
+        "ms": round(ms_f, 3), "TFLOP/s": round(fl / ms_f / 1e9, 1)}
     # the GEMM alone (largest layer), against cuBLAS-free denominators: measured bf16 peak / 2 for tf32
     th, tw = torch.randn(8192, 4096, device="cuda"), torch.randn(4096, 4096, device="cuda")
     hh, ww, cc = w(th, F32), w(tw, F32), Tensor.empty((8192, 4096), F32, dev)

@@ -54,8 +54,32 @@ for _member, _fn in {"Abs": "abs", "Sgn": "sgn", "Log": "log", "Log10": "log10",
     setattr(Expr, _fn, (lambda m: lambda self: self._un(m))(_member))
 
 
+_CACHE: Dict[tuple, list] = {}
+
+
 def trace(fn: Callable, nsrc: int) -> List[Tuple[int, int, int, int, int, float]]:
-    """Returns [(kind, op, dst, a, b, imm)] for `fn` applied to `nsrc` sources."""
+    """Returns [(kind, op, dst, a, b, imm)] for `fn` applied to `nsrc` sources. Traces are cached per code object
+    and captured constants, so a training loop pays for tracing once."""
+    key = None
+    code = getattr(fn, "__code__", None)
+    if code is not None:
+        try:
+            cells = tuple(c.cell_contents for c in (fn.__closure__ or ()))
+            key = (code, cells, fn.__defaults__, nsrc)
+            hash(key)
+        except (TypeError, ValueError):
+            key = None
+    if key is not None and key in _CACHE:
+        return _CACHE[key]
+    prog = _trace(fn, nsrc)
+    if key is not None:
+        if len(_CACHE) > 512:
+            _CACHE.clear()
+        _CACHE[key] = prog
+    return prog
+
+
+def _trace(fn: Callable, nsrc: int) -> List[Tuple[int, int, int, int, int, float]]:
     root = Expr.lift(fn(*[Expr("src", src=i) for i in range(nsrc)]))
     if root.kind == "src":
         root = root._un("UnaryPlus")

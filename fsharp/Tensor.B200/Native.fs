@@ -107,6 +107,13 @@ module Native =
     extern DnStatus dn_batched_mat_mat_dot(DnTensor& t, DnTensor& a, DnTensor& b)
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern DnStatus dn_batched_invert(DnTensor& t, DnTensor& a)
+    /// dn_fused_instr: kind (0 unary, 1 binary, 2 const), op, dst, a, b, imm — see include/dn_tensor.h
+    [<Struct; StructLayout(LayoutKind.Sequential)>]
+    type DnFusedInstr =
+        val mutable Kind: int; val mutable Op: int; val mutable Dst: int; val mutable A: int; val mutable B: int
+        val mutable Imm: double
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern DnStatus dn_fused_elemwise(DnTensor& t, nativeint[] srcs, int nsrc, DnFusedInstr[] prog, int ninstr)
 
     /// Maps a non-OK status to the exception the reference raises in the same situation (SURVEY.md §8b).
     let check (st: DnStatus) =

@@ -160,7 +160,7 @@ struct CudaApi {
     DN_FWD(fill_const) DN_FWD(fill_incrementing) DN_FWD(copy) DN_FWD(convert) DN_FWD(unary) DN_FWD(binary) DN_FWD(compare)
     DN_FWD(is_finite) DN_FWD(if_then_else) DN_FWD(reduce_last_axis) DN_FWD(arg_reduce_last_axis) DN_FWD(find_last_axis)
     DN_FWD(gather) DN_FWD(scatter) DN_FWD(count_true) DN_FWD(masked_get) DN_FWD(masked_set) DN_FWD(true_indices)
-    DN_FWD(vec_vec_dot) DN_FWD(mat_vec_dot) DN_FWD(mat_mat_dot) DN_FWD(batched_mat_mat_dot) DN_FWD(batched_invert)
+    DN_FWD(vec_vec_dot) DN_FWD(mat_vec_dot) DN_FWD(mat_mat_dot) DN_FWD(batched_mat_mat_dot) DN_FWD(batched_invert) DN_FWD(fused_elemwise)
 #undef DN_FWD
 };
 
@@ -215,6 +215,12 @@ struct Backend {
     }
     template <class TT, class TA, class TB> static void BatchedMatMatDot(const TT &t, const TA &a, const TB &b) {
         auto x = d(t), y = d(a), z = d(b); Api::check(Api::batched_mat_mat_dot(&x, &y, &z));
+    }
+    // FusedElemwise (extension, include/dn_tensor.h dn_fused_elemwise)
+    template <class TT> static void FusedElemwise(const TT &t, const std::vector<const dn_tensor *> &srcs,
+                                                  const std::vector<dn_fused_instr> &prog) {
+        auto x = d(t);
+        Api::check(Api::fused_elemwise(&x, srcs.data(), (int32_t)srcs.size(), prog.data(), (int32_t)prog.size()));
     }
     // BatchedInvert (TensorBackend.fs:142)
     template <class TT, class TA> static void BatchedInvert(const TT &t, const TA &a) {

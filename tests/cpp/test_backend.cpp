@@ -38,6 +38,7 @@ DNO(mat_vec_dot, const dn_tensor *, const dn_tensor *, const dn_tensor *)
 DNO(mat_mat_dot, const dn_tensor *, const dn_tensor *, const dn_tensor *)
 DNO(batched_mat_mat_dot, const dn_tensor *, const dn_tensor *, const dn_tensor *)
 DNO(batched_invert, const dn_tensor *, const dn_tensor *)
+DNO(fused_elemwise, const dn_tensor *, const dn_tensor *const *, int32_t, const dn_fused_instr *, int32_t)
 #undef DNO
 }
 
@@ -53,7 +54,7 @@ struct OracleApi {
     DN_FWD(fill_const) DN_FWD(fill_incrementing) DN_FWD(copy) DN_FWD(convert) DN_FWD(unary) DN_FWD(binary) DN_FWD(compare)
     DN_FWD(is_finite) DN_FWD(if_then_else) DN_FWD(reduce_last_axis) DN_FWD(arg_reduce_last_axis) DN_FWD(find_last_axis)
     DN_FWD(gather) DN_FWD(scatter) DN_FWD(count_true) DN_FWD(masked_get) DN_FWD(masked_set) DN_FWD(true_indices)
-    DN_FWD(vec_vec_dot) DN_FWD(mat_vec_dot) DN_FWD(mat_mat_dot) DN_FWD(batched_mat_mat_dot) DN_FWD(batched_invert)
+    DN_FWD(vec_vec_dot) DN_FWD(mat_vec_dot) DN_FWD(mat_mat_dot) DN_FWD(batched_mat_mat_dot) DN_FWD(batched_invert) DN_FWD(fused_elemwise)
 #undef DN_FWD
 };
 
@@ -152,6 +153,15 @@ Results run_suite() {
         for (size_t i = 0; i < sq.size(); ++i) sq[i] = uni(gen) / 50.f + ((i % (40 * 40)) % 41 == 0 ? 21.f : 0.f);
         r["invert"] = dbl(TF::ofVector(sq, {3, 40, 40}).invert().toVector());
     }
+    {   // fused a*b + sin(a) == the three-call sequence
+        TF fused(A.Shape());
+        const dn_tensor da = A.Desc(), db = Bm.Desc();
+        Backend<Api>::FusedElemwise(fused, {&da, &db}, {{DN_FUSED_BINARY, DN_MULTIPLY, 2, 0, 1, 0.0}, {DN_FUSED_UNARY, DN_SIN, 3, 0, 0, 0.0},
+                                                {DN_FUSED_BINARY, DN_ADD, 2, 2, 3, 0.0}});
+        r["fused"] = dbl(fused.toVector());
+        r["unfused"] = dbl((A * Bm + A.unary(DN_SIN)).toVector());
+        expect(r["fused"] == r["unfused"], id + " fused a*b+sin(a) is bit-identical to the three-call sequence");
+    }
     A.FillMultiply(A, Bm);                  // in place (Guide-Operations.md:112-117)
     r["inplace"] = dbl(A.toVector());
     return r;
@@ -170,6 +180,7 @@ int main(int argc, char **argv) {
             if (k == "sum1" || k == "sum0") { rtol = 1e-3; atol = 0.05; }
             if (k == "dot") { rtol = 1e-2; atol = 25.0; }  // TF32 tensor cores, |a|.|b| ~ 8e4 per element
             if (k == "invert") { rtol = 1e-4; atol = 1e-6; }
+            if (k == "fused" || k == "unfused") { rtol = 1e-5; atol = 1e-4; }
             expect(close(cuda[k], kv.second, rtol, atol), "cuda vs host: " + k);
         }
     }

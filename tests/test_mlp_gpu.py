@@ -55,3 +55,23 @@ def test_mlp_step_full_size_properties(cuda_dev):
         recomputed = float(-(tn * np.log(np.maximum(pn, 1e-45))).sum(axis=1).mean())
         assert abs(recomputed - losses[-1]) <= 1e-3 * abs(recomputed) + 1e-5
     assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
+
+
+def test_mlp_step_fused_equals_unfused(cuda_dev):
+    """The FusedElemwise variant of the training step must produce the SAME bits as the operator-by-operator step
+    on the device (every fused instruction rounds like the operator it replaces; the GEMMs are the same calls)."""
+    sizes, batch = (64, 96, 80, 10), 256
+    rng = np.random.default_rng(53)
+    p0 = init_params(rng, sizes)
+    xn, tn = synthetic_batch(rng, batch, sizes[0], sizes[-1])
+    outs = []
+    for fused in (False, True):
+        params = [(CudaTensor.ofNumpy(w.copy()), CudaTensor.ofNumpy(b.copy())) for w, b in p0]
+        x, t = CudaTensor.ofNumpy(xn), CudaTensor.ofNumpy(tn)
+        for _ in range(3):
+            loss, pred = train_step(x, t, params, 0.05, fused=fused)
+        outs.append((float(loss.Value), pred.toNumpy(), [(w.toNumpy(), b.toNumpy()) for w, b in params]))
+    (l0, p0_, w0), (l1, p1_, w1) = outs
+    assert l0 == l1 and np.array_equal(p0_, p1_)
+    for (wa, ba), (wb, bb) in zip(w0, w1):
+        assert np.array_equal(wa, wb) and np.array_equal(ba, bb)
