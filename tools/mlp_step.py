@@ -141,6 +141,9 @@ def main():
     fl = flops_per_step(batch, sizes)
     print(f"C5 MLP 784-4096-4096-10 batch 8192: {ms:.3f} ms/step, {fl / ms / 1e9:.1f} TFLOP/s (GEMM flops "
           f"{fl / 1e12:.3f} TFLOP/step), {(dev.LaunchCount() - l0) // n} kernel launches/step, losses {losses}")
+    for _ in range(2):  # warm-up: the first launch of a kernel loads its module (CUDA lazy loading)
+        train_step(x, t, params, 0.01, fused=True)
+    torch.cuda.synchronize()
     l0 = dev.LaunchCount()
     s.record()
     for _ in range(n):
