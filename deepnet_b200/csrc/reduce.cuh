@@ -97,6 +97,17 @@ template <class T> __device__ __forceinline__ T shfl_xor_any(T v, int m) {
     }
 }
 
+template <class T> __device__ __forceinline__ T shfl_idx_any(T v, int src) {
+    constexpr int N = (sizeof(T) + 3) / 4;
+    unsigned u[N] = {};
+    memcpy(u, &v, sizeof(T));
+#pragma unroll
+    for (int i = 0; i < N; ++i) u[i] = __shfl_sync(kFull, u[i], src);
+    T r;
+    memcpy(&r, u, sizeof(T));
+    return r;
+}
+
 template <class T>
 struct SumOp {
     using In = T; using Out = T; using State = T;
@@ -452,6 +463,39 @@ __global__ void __launch_bounds__(kRedThreads) reduce_finalize_kernel(const __gr
     *reinterpret_cast<Out *>(p.dst + toff) = Op::finalize(acc);
 }
 
+// The same for rows shared by MANY CTAs (whole-tensor folds: up to 1024 partials per row): one warp per row, lane l
+// folds the contiguous block l of the partials (independent loads in flight), the 32 lane results are combined in
+// lane order — still an ordered fold, without a chain of ~1000 dependent L2 round trips in one thread.
+template <class Op>
+__global__ void __launch_bounds__(kRedThreads) reduce_finalize_warp_kernel(const __grid_constant__ RedParams p) {
+    using State = typename Op::State;
+    using Out = typename Op::Out;
+    const int lane = threadIdx.x & 31;
+    const uint64_t r = (uint64_t)blockIdx.x * kRedWarps + (threadIdx.x >> 5);
+    if (r >= p.nrows) return;
+    const State *part = reinterpret_cast<const State *>(p.partials) + r * p.ctas_per_row;
+    const int per = (p.ctas_per_row + 31) / 32;
+    const int b = lane * per;
+    int e = b + per;
+    if (e > p.ctas_per_row) e = p.ctas_per_row;
+    State acc = Op::identity();
+    bool any = false;
+    for (int k = b; k < e; ++k) {
+        const State v = part[k];
+        acc = any ? Op::combine(acc, v) : v;
+        any = true;
+    }
+    // ordered combine over the lanes that hold something (lane order == partial order)
+    State total = shfl_idx_any(acc, 0);
+    const int used = (p.ctas_per_row + per - 1) / per;
+    for (int l = 1; l < used; ++l) total = Op::combine(total, shfl_idx_any(acc, l));
+    if (lane == 0) {
+        int64_t soff, toff;
+        red_offsets(p.outer, (uint32_t)r, soff, toff);
+        *reinterpret_cast<Out *>(p.dst + toff) = Op::finalize(total);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // cols family: blockDim = (TX, TY); thread (x, y) folds chunk y of output x sequentially.
 // ---------------------------------------------------------------------------------------------------------------
@@ -578,7 +622,7 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
                 DN_LAUNCH((reduce_rows_kernel<Op>), (unsigned)ctas, kRedThreads, 0, p, op);
             } else {
                 // S CTAs per row so that rc*S CTAs fill the machine; every part stays >= 4 KiB
-                int64_t S = (2 * (int64_t)sms + rc - 1) / rc;
+                int64_t S = (6 * (int64_t)sms + rc - 1) / rc;
                 const int64_t max_s = bytes / (kRedWarps * 4096);
                 if (S > max_s) S = max_s;
                 if (S < 1) S = 1;
@@ -599,7 +643,9 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
                 const int64_t cap = (int64_t)sms * 16;
                 if (ctas > cap) ctas = cap;
                 DN_LAUNCH((reduce_rows_kernel<Op>), (unsigned)ctas, kRedThreads, 0, p, op);
-                if (S > 1) {
+                if (S >= 32) {
+                    DN_LAUNCH((reduce_finalize_warp_kernel<Op>), (unsigned)((rc + kRedWarps - 1) / kRedWarps), kRedThreads, 0, p);
+                } else if (S > 1) {
                     DN_LAUNCH((reduce_finalize_kernel<Op>), (unsigned)((rc + kRedThreads - 1) / kRedThreads),
                               kRedThreads, 0, p);
                 }
