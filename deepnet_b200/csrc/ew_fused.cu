@@ -15,9 +15,10 @@ using namespace dn;
 
 namespace {
 
-struct FusedInstr {
-    uint8_t kind, op, dst, a, b;
-};
+// One instruction per 32-bit word: bits 0-1 kind, 2-7 op, 8-11 dst, 12-15 a, 16-19 b (one load per decode).
+__host__ __device__ constexpr uint32_t fused_pack(int kind, int op, int dst, int a, int b) {
+    return (uint32_t)kind | ((uint32_t)op << 2) | ((uint32_t)dst << 8) | ((uint32_t)a << 12) | ((uint32_t)b << 16);
+}
 
 template <class T, int NS>
 struct FusedSig;
@@ -35,7 +36,7 @@ struct FusedF : FusedSig<T, NS>::type {
     static constexpr int MaxInFlight = 4;
     static constexpr int MinBlocks = 4;    // 24 KiB of register-file slots per CTA
     int32_t n;
-    FusedInstr ins[DN_FUSED_MAX_INSTRS];
+    uint32_t ins[DN_FUSED_MAX_INSTRS];
     T imm[DN_FUSED_MAX_INSTRS];
 
     template <int OP, int VEC>
@@ -80,15 +81,16 @@ struct FusedF : FusedSig<T, NS>::type {
         T z[VEC];
 #pragma unroll 1
         for (int k = 0; k < n; ++k) {
-            const FusedInstr in = ins[k];
+            const uint32_t w = ins[k];
+            const int kind = w & 3, op = (w >> 2) & 63, dst = (w >> 8) & 15, ra = (w >> 12) & 15, rb = (w >> 16) & 15;
             T x[VEC], y[VEC];
-            if (in.kind == DN_FUSED_CONST) {
+            if (kind == DN_FUSED_CONST) {
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) z[e] = imm[k];
             } else {
-                get(in.a, x);
-                if (in.kind == DN_FUSED_UNARY) {
-                    switch (in.op) {
+                get(ra, x);
+                if (kind == DN_FUSED_UNARY) {
+                    switch (op) {
 #define DN_U(OP) case OP: unary_all<OP, VEC>(z, x); break;
                         DN_U(DN_UNARY_MINUS) DN_U(DN_ABS) DN_U(DN_SGN) DN_U(DN_LOG) DN_U(DN_LOG10) DN_U(DN_EXP) DN_U(DN_SIN)
                         DN_U(DN_COS) DN_U(DN_TAN) DN_U(DN_ASIN) DN_U(DN_ACOS) DN_U(DN_ATAN) DN_U(DN_SINH) DN_U(DN_COSH)
@@ -99,8 +101,8 @@ struct FusedF : FusedSig<T, NS>::type {
                         for (int e = 0; e < VEC; ++e) z[e] = x[e];
                     }
                 } else {
-                    get(in.b, y);
-                    switch (in.op) {
+                    get(rb, y);
+                    switch (op) {
 #define DN_B(OP) case OP: binary_all<OP, VEC>(z, x, y); break;
                         DN_B(DN_SUBTRACT) DN_B(DN_MULTIPLY) DN_B(DN_DIVIDE) DN_B(DN_MODULO) DN_B(DN_POWER)
                         DN_B(DN_MAX_ELEMWISE) DN_B(DN_MIN_ELEMWISE)
@@ -109,7 +111,7 @@ struct FusedF : FusedSig<T, NS>::type {
                     }
                 }
             }
-            put(in.dst, z);
+            put(dst, z);
         }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) out[e] = z[e];  // the last instruction's value
@@ -130,10 +132,11 @@ dn_status run_fused(EwPlan &plan, const dn_fused_instr *prog, int n) {
     FusedF<T, NS> f;
     f.n = n;
     for (int k = 0; k < DN_FUSED_MAX_INSTRS; ++k) {
-        f.ins[k] = FusedInstr{0, 0, 0, 0, 0};
+        f.ins[k] = 0;
         f.imm[k] = T(0);
         if (k < n) {
-            f.ins[k] = FusedInstr{(uint8_t)prog[k].kind, (uint8_t)prog[k].op, (uint8_t)prog[k].dst, (uint8_t)prog[k].a, (uint8_t)prog[k].b};
+            const bool reads_b = prog[k].kind == DN_FUSED_BINARY, reads_a = prog[k].kind != DN_FUSED_CONST;
+            f.ins[k] = fused_pack(prog[k].kind, prog[k].op, prog[k].dst, reads_a ? prog[k].a : 0, reads_b ? prog[k].b : 0);
             f.imm[k] = (T)prog[k].imm;
         }
     }
