@@ -213,6 +213,10 @@ struct EwSig {
     // VectorEval functors evaluate a whole work item at once: `eval(Out (&r)[VEC], const In0 (&a)[VEC], ...)`
     // (the fused-expression interpreter amortises its instruction decode over the VEC elements).
     static constexpr bool VectorEval = false;
+    // MultiEval functors evaluate ALL U work items of a thread in one call:
+    // `eval_multi<VEC, U>(Pack<Out,VEC> (&r)[U], const P0 (&a)[U], const P1 (&b)[U], const P2 (&c)[U])`
+    // (the interpreter then decodes every program instruction once per thread iteration, not once per item).
+    static constexpr bool MultiEval = false;
     static constexpr int MaxInFlight = 8;  // cap on U, the work items a thread keeps in flight
     static constexpr int MinBlocks = 1;    // __launch_bounds__ minimum resident CTAs per SM
 };
@@ -279,6 +283,16 @@ __global__ void __launch_bounds__(kEwThreads, F::MinBlocks) ew_kernel(const __gr
                 if constexpr (F::NSRC > 2) c[j].load(p.ptr[3] + off[3], (p.splat_mask >> 3) & 1, wide, VEC > 1 && ((p.rev_mask >> 3) & 1));
             }
         }
+        if constexpr (F::MultiEval) {
+            // inactive items compute on whatever their registers hold; only active results are stored
+            Pack<Out, VEC> r[U];
+            f.template eval_multi<VEC, U>(r, a, b, c);
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const uint64_t idx = base + (uint32_t)j * kEwThreads + threadIdx.x;
+                if (idx < p.n) store_pack(p.ptr[0] + toff[j], r[j], wide);
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const uint64_t idx = base + (uint32_t)j * kEwThreads + threadIdx.x;
@@ -308,6 +322,7 @@ __global__ void __launch_bounds__(kEwThreads, F::MinBlocks) ew_kernel(const __gr
                 store_pack(p.ptr[0] + toff[j], r, wide);
             }
         }
+        }  // !MultiEval
     }
 }
 

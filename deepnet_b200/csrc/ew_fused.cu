@@ -33,8 +33,9 @@ struct FusedF : FusedSig<T, NS>::type {
     // 16-byte work items = one register-file slot; consecutive lanes still write consecutive 16-byte pieces,
     // i.e. whole sectors per warp-level store
     static constexpr int Vec = 16 / (int)sizeof(T);
-    static constexpr int MaxInFlight = 4;
-    static constexpr int MinBlocks = 4;    // 24 KiB of register-file slots per CTA
+    static constexpr bool MultiEval = true;   // decode once per thread iteration for both items in flight
+    static constexpr int MaxInFlight = 2;
+    static constexpr int MinBlocks = 4;       // 48 KiB of register-file slots per CTA (6 registers x 2 items)
     int32_t n;
     uint32_t ins[DN_FUSED_MAX_INSTRS];
     T imm[DN_FUSED_MAX_INSTRS];
@@ -115,6 +116,79 @@ struct FusedF : FusedSig<T, NS>::type {
         }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) out[e] = z[e];  // the last instruction's value
+    }
+
+    // All U work items of the thread at once: one decode per program instruction, U slots per virtual register.
+    template <int VEC, int U, class PA, class PB, class PC>
+    __device__ __forceinline__ void eval_multi(Pack<T, VEC> (&out)[U], const PA (&sa)[U], const PB (&sb)[U], const PC (&sc)[U]) const {
+        static_assert(VEC <= kSlotElems && U <= 2, "register-file geometry");
+        __shared__ Slot rf[DN_FUSED_REGS][2][kEwThreads];
+        const int tid = threadIdx.x;
+        auto put = [&](int reg, int j, const T (&v)[VEC]) {
+            Slot sl;
+#pragma unroll
+            for (int e = 0; e < kSlotElems; ++e) sl.v[e] = e < VEC ? v[e] : T(0);
+            rf[reg][j][tid] = sl;
+        };
+        auto get = [&](int reg, int j, T (&v)[VEC]) {
+            const Slot sl = rf[reg][j][tid];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[e] = sl.v[e];
+        };
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            put(0, j, sa[j].p.v);
+            if constexpr (NS > 1) put(1, j, sb[j].p.v);
+            if constexpr (NS > 2) put(2, j, sc[j].p.v);
+        }
+        T z[U][VEC];
+#pragma unroll 1
+        for (int k = 0; k < n; ++k) {
+            const uint32_t w = ins[k];
+            const int kind = w & 3, op = (w >> 2) & 63, dst = (w >> 8) & 15, ra = (w >> 12) & 15, rb = (w >> 16) & 15;
+            T x[U][VEC], y[U][VEC];
+            if (kind == DN_FUSED_CONST) {
+#pragma unroll
+                for (int j = 0; j < U; ++j)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) z[j][e] = imm[k];
+            } else {
+#pragma unroll
+                for (int j = 0; j < U; ++j) get(ra, j, x[j]);
+                if (kind == DN_FUSED_UNARY) {
+                    switch (op) {
+#define DN_U(OP) case OP: _Pragma("unroll") for (int j = 0; j < U; ++j) unary_all<OP, VEC>(z[j], x[j]); break;
+                        DN_U(DN_UNARY_MINUS) DN_U(DN_ABS) DN_U(DN_SGN) DN_U(DN_LOG) DN_U(DN_LOG10) DN_U(DN_EXP) DN_U(DN_SIN)
+                        DN_U(DN_COS) DN_U(DN_TAN) DN_U(DN_ASIN) DN_U(DN_ACOS) DN_U(DN_ATAN) DN_U(DN_SINH) DN_U(DN_COSH)
+                        DN_U(DN_TANH) DN_U(DN_SQRT) DN_U(DN_CEILING) DN_U(DN_FLOOR) DN_U(DN_ROUND) DN_U(DN_TRUNCATE)
+#undef DN_U
+                    default:
+#pragma unroll
+                        for (int j = 0; j < U; ++j)
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) z[j][e] = x[j][e];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < U; ++j) get(rb, j, y[j]);
+                    switch (op) {
+#define DN_B(OP) case OP: _Pragma("unroll") for (int j = 0; j < U; ++j) binary_all<OP, VEC>(z[j], x[j], y[j]); break;
+                        DN_B(DN_SUBTRACT) DN_B(DN_MULTIPLY) DN_B(DN_DIVIDE) DN_B(DN_MODULO) DN_B(DN_POWER)
+                        DN_B(DN_MAX_ELEMWISE) DN_B(DN_MIN_ELEMWISE)
+#undef DN_B
+                    default:
+#pragma unroll
+                        for (int j = 0; j < U; ++j) binary_all<DN_ADD, VEC>(z[j], x[j], y[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) put(dst, j, z[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) out[j].v[e] = z[j][e];
     }
 
     // element-at-a-time form (not used by the kernels this functor is instantiated for, required by the interface)
