@@ -176,6 +176,40 @@ class Tensor:
             raise ValueError("Need at least a matrix to extract diagonal")
         return self.diagAxis(self.NDims - 2, self.NDims - 1)
 
+    @staticmethod
+    def diagMatAxis(ax1: int, ax2: int, a: "Tensor") -> "Tensor":
+        """Tensor.diagMatAxis, Tensor.fs:4140-4151: a new tensor with `a` on the diagonal over (ax1, ax2), zero elsewhere."""
+        if ax1 == ax2:
+            raise ValueError("axes to use for diagonal must be different")
+        ax1, ax2 = (ax1, ax2) if ax1 < ax2 else (ax2, ax1)
+        if not (0 <= ax1 < a.NDims):
+            raise ValueError(f"Specified axis {ax1} is invalid for tensor of shape {a.Shape}.")
+        if not (0 <= ax2 <= a.NDims):
+            raise ValueError(f"Cannot insert axis at position {ax2} into array of shape {a.Shape}.")
+        shp = list(a.Shape)
+        shp.insert(ax2, a.Shape[ax1])
+        d = Tensor.zeros(shp, a.DataType, a.Dev)
+        d.diagAxis(ax1, ax2).CopyFrom(a)
+        return d
+
+    @staticmethod
+    def diagMat(a: "Tensor") -> "Tensor":
+        """Tensor.diagMat, Tensor.fs:4168-4171."""
+        if a.NDims < 1:
+            raise ValueError("need at leat a one-dimensional array to create a diagonal matrix")
+        return Tensor.diagMatAxis(a.NDims - 1, a.NDims, a)
+
+    def traceAxis(self, ax1: int, ax2: int) -> "Tensor":
+        """Tensor.traceAxis, Tensor.fs:4188-4190: sum over the diagonal view."""
+        tax = ax1 if ax1 < ax2 else ax1 - 1
+        return self.diagAxis(ax1, ax2).sumAxis(tax)
+
+    def trace(self) -> "Tensor":
+        """Tensor.trace, Tensor.fs:4206-4209."""
+        if self.NDims < 2:
+            raise ValueError(f"Need at least a two dimensional array for trace but got shape {self.Shape}.")
+        return self.traceAxis(self.NDims - 2, self.NDims - 1)
+
     def tryReshapeView(self, shp) -> Optional["Tensor"]:
         lay = TL.tryReshape(shp, self._layout)
         return None if lay is None else self.Relayout(lay)

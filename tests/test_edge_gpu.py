@@ -137,3 +137,24 @@ def test_concurrent_threads_with_their_own_streams(cuda_dev):
             assert h.shape == c.shape and (h == c).all(), key
         np.testing.assert_allclose(out["cuda"][5], out["host"][5], rtol=1e-10, atol=1e-12)
         np.testing.assert_allclose(out["cuda"][6], out["host"][6], rtol=1e-10, atol=1e-10)
+
+
+def test_reference_diag_and_trace_tests(cuda_dev):
+    """Tensor.Test/BaseTests.fs:128-158 on the CUDA device: diagMat writes through a diagonal view (stride n+1),
+    trace reduces over one; results equal the host's bit for bit (integers) / exactly (copied floats)."""
+    from deepnet_b200 import Tensor
+    from oracle.host_tensor import HostTensor
+    rng = np.random.default_rng(77)
+    v = rng.uniform(-5, 5, size=(4, 33)).astype(np.float32)
+    i = rng.integers(-100, 100, size=(5, 7, 65)).astype(np.int64)
+    for arr in (v, i):
+        h, c = HostTensor.ofNumpy(arr), CudaTensor.ofNumpy(arr)
+        hd, cd = Tensor.diagMat(h), Tensor.diagMat(c)
+        assert cd.Shape == arr.shape + (arr.shape[-1],)
+        assert np.array_equal(cd.toNumpy(), hd.toNumpy())
+        assert np.array_equal(cd.diag().toNumpy(), arr)
+        if arr.dtype == np.int64:
+            assert np.array_equal(cd.trace().toNumpy(), c.sumAxis(arr.ndim - 1).toNumpy())
+            assert np.array_equal(cd.trace().toNumpy(), hd.trace().toNumpy())
+        else:
+            np.testing.assert_allclose(cd.trace().toNumpy(), hd.trace().toNumpy(), rtol=1e-5, atol=1e-4)

@@ -42,3 +42,17 @@ def test_oracle_invert_against_numpy():
             assert np.abs(back - m).max() <= 10 * tol
     with pytest.raises(SingularMatrixException):
         Tensor.invert(HostTensor.ofNumpy(np.array([[1.0, 0.0, 0.0], [1.0, 2.0, 0.0], [1.0, 0.0, 0.0]])))
+
+
+def test_reference_diag_and_trace_tests_on_oracle():
+    """Tensor.Test/BaseTests.fs:128-158 (`Build and extract diagonal`, `Batched trace`) on the HostTensor oracle."""
+    import numpy as np
+    from deepnet_b200 import Tensor
+    from oracle.host_tensor import HostTensor
+    v = HostTensor.ofNumpy(np.array([1.0, 2.0, 3.0]))
+    dm = Tensor.diagMat(v)
+    assert np.array_equal(dm.toNumpy(), np.diag([1.0, 2.0, 3.0])) and np.array_equal(dm.diag().toNumpy(), v.toNumpy())
+    vb = HostTensor.ofNumpy(np.array([[1, 2, 3], [4, 5, 6]], dtype=np.int32))
+    dmb = Tensor.diagMat(vb)
+    assert dmb.Shape == (2, 3, 3)
+    assert np.array_equal(dmb.trace().toNumpy(), vb.sumAxis(1).toNumpy())
