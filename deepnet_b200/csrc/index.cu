@@ -5,15 +5,16 @@
 // (CudaBackend.fs:489-492 raise NotSupportedException); their semantics are the host's (ScalarOps.fs:667-707):
 // walk the tensor in LOGICAL row-major order of the view, whatever its strides.
 //
-// Ordered compaction: one single-pass primitive shared by TrueIndices, MaskedGet and MaskedSet. Every CTA draws
-// tiles of 8192 consecutive logical positions from a ticket counter (thread = 16 consecutive positions, one
-// 128-bit load when they are contiguous in memory), ranks its true elements with a register popcount + shuffle
-// scan, obtains the number of true elements in all earlier tiles by decoupled look-back over a 64-bit
-// {status, count} word per tile (the mask is read from HBM exactly once, no count pass, no scan kernel), stages
-// the selected positions in shared memory so that consecutive threads own consecutive ranks, and hands
-// (rank, logical position) to a sink: coordinates (TrueIndices), source -> dense target (MaskedGet), dense
-// values -> target (MaskedSet), or a plain index list (per-dimension masks, which select a cartesian product:
-// ScalarOps.fs:672-681). Sinks are two-phase (load, store) so that four independent loads are in flight per thread.
+// Ordered compaction: one single-pass primitive shared by TrueIndices, MaskedGet and MaskedSet. Every CTA draws a
+// tile of 8192 or 32768 consecutive logical positions from a ticket counter (thread = 16 consecutive positions
+// per chunk, one 128-bit load when they are contiguous in memory, all loads of the tile issued back to back), ranks
+// its true elements with a register popcount + shuffle scan, obtains the number of true elements in all earlier
+// tiles by decoupled look-back over a 64-bit {status, count} word per tile (the mask is read from HBM exactly once,
+// no count pass, no scan kernel), stages the selected positions in shared memory so that consecutive threads own
+// consecutive ranks, and hands (rank, logical position) to a sink: coordinates (TrueIndices), source -> dense
+// target (MaskedGet), dense values -> target (MaskedSet), or a plain index list (per-dimension masks, which select
+// a cartesian product: ScalarOps.fs:672-681). Sinks are two-phase (load, store) so that four independent loads are
+// in flight per thread; MaskedGet's source loads are issued before the look-back returns.
 #include <cstdlib>
 
 #include "ew_ops.cuh"
