@@ -74,7 +74,16 @@ class NativeTensorBackend:
     # -- descriptor marshalling ------------------------------------------------------------------------------
     @staticmethod
     def _d(t) -> native.dn_tensor:
-        return native.make_desc(t.Storage.BasePtr(), t.Layout, t.DataType)
+        """The dn_tensor descriptor of a frontend. A Tensor's layout and storage never change after construction,
+        and the native side treats descriptors as const, so the descriptor is built once per Tensor object."""
+        d = getattr(t, "_desc", None)
+        if d is None:
+            d = native.make_desc(t.Storage.BasePtr(), t.Layout, t.DataType)
+            try:
+                t._desc = d
+            except AttributeError:
+                pass
+        return d
 
     def _call(self, name, *args):
         self.api.call(name, *args)
