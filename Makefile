@@ -33,7 +33,7 @@ all: $(LIB)
 
 $(LIB): $(OBJECTS)
 	@mkdir -p $(dir $@)
-	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $(OBJECTS) -lcudart -lcuda
+	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $(OBJECTS) -lcudart
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HEADERS)
 	@mkdir -p $(OBJ)

@@ -249,30 +249,17 @@ class TensorCudaBackend(NativeTensorBackend):
         self._call("set_item", d, pos, p)
 
     def Transfer(self, trgt, src) -> bool:
-        """CudaBackend.fs:206-270: host<->device copy of C-contiguous blocks; anything else is made contiguous
-        first by the frontend. Returns False when this backend cannot do the transfer."""
+        """CudaBackend.fs:206-270. Any pair of views: the layout handling (strided pack of the host side, strided
+        copy on the device) is native — dn_transfer_h2d / dn_transfer_d2h. Returns False when this backend cannot
+        do the transfer (both or neither side on the device)."""
         t_cuda = isinstance(trgt.Storage, TensorCudaStorage)
         s_cuda = isinstance(src.Storage, TensorCudaStorage)
         if t_cuda == s_cuda:
             return False
-        if not TL.isC(src.Layout):
-            src = src.Copy()
-        if not TL.isC(trgt.Layout):
-            tmp = type(trgt).empty(trgt.Shape, trgt.DataType, trgt.Dev)
-            if not self.Transfer(tmp, src):
-                return False
-            trgt.CopyFrom(tmp)
-            return True
-        nbytes = src.NElems * dtypes.itemsize(src.DataType)
-        if nbytes == 0:
-            return True
-        isz = dtypes.itemsize(src.DataType)
         if t_cuda:
-            self._call("memcpy_h2d", trgt.Storage.BasePtr() + trgt.Layout.Offset * isz,
-                       src.Storage.BasePtr() + src.Layout.Offset * isz, nbytes)
+            self._call("transfer_h2d", self._d(trgt), self._d(src))
         else:
-            self._call("memcpy_d2h", trgt.Storage.BasePtr() + trgt.Layout.Offset * isz,
-                       src.Storage.BasePtr() + src.Layout.Offset * isz, nbytes)
+            self._call("transfer_d2h", self._d(trgt), self._d(src))
         return True
 
 

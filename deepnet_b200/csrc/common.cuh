@@ -53,6 +53,14 @@ inline dn_status launch_status(const char *what) {
     return DN_OK;
 }
 
+// Sharded launches (shard.cu, peer.cuh): the peer-store / exit-barrier block that the NEXT output-storing kernel
+// launched by this thread has to carry. peer_take moves it into `out` and clears it (false: plain launch).
+struct PeerSync;
+bool peer_take(PeerSync &out);
+
+// countTrue of a bool view into a device counter on the current stream, without a read-back (index.cu).
+dn_status count_true_async(const dn_tensor *a, unsigned long long *dev_total);
+
 // Stream-ordered scratch memory for multi-pass kernels (partials, block counts).
 dn_status scratch_alloc(size_t nbytes, void **ptr);
 void scratch_free(void *ptr);

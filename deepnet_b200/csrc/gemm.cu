@@ -369,11 +369,15 @@ dn_status repack_kmajor(Operand2D &o, void **scratch) {
 template <int BN, bool A_MN, bool B_MN>
 dn_status launch_tf32(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p) {
     using Cfg = GemmCfg<BN>;
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE function attribute: one flag per device
+    // (a process may drive several devices, dn_set_device / dn_shard_*), set at most once each
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    DN_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         DN_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = tiles < sm_count() ? tiles : sm_count();

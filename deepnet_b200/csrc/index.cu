@@ -835,6 +835,23 @@ dn_status masked_general(const dn_tensor *dense, const dn_tensor *full, const dn
 
 }  // namespace
 
+namespace dn {
+// countTrue of a bool view into a device counter, stream-ordered (no read-back). Used by dn_count_true and by the
+// sharded compaction (shard.cu), which publishes the count to the peers without a host round trip.
+dn_status count_true_async(const dn_tensor *a, unsigned long long *dev_total) {
+    if (!tensor_valid(a) || a->dtype != DN_BOOL) return set_error(DN_ERR_INVALID_ARG, "countTrue: bad argument");
+    DN_CUDA_TRY(cudaMemsetAsync(dev_total, 0, sizeof(unsigned long long), current_stream()));
+    BoolView m;
+    dn_status st = make_bool_view(m, a, "countTrue");
+    if (st != DN_OK) return st;
+    if (m.n == 0) return DN_OK;
+    merge_bool_view(m);
+    const uint32_t nblocks = (uint32_t)(((uint64_t)m.n + kIdxThreads * kItems - 1) / (kIdxThreads * kItems));
+    DN_LAUNCH(mask_count_kernel, tiles_grid(nblocks, 16), kIdxThreads, 0, m, dev_total);
+    return launch_status("countTrue kernel");
+}
+}  // namespace dn
+
 extern "C" {
 
 dn_status dn_gather(const dn_tensor *t, const dn_tensor *const *idxs, int32_t nidxs, const dn_tensor *a) {
@@ -908,21 +925,18 @@ dn_status dn_scatter(const dn_tensor *t, const dn_tensor *const *idxs, int32_t n
 dn_status dn_count_true(const dn_tensor *a, int64_t *count) {
     if (!tensor_valid(a) || !count || a->dtype != DN_BOOL) return set_error(DN_ERR_INVALID_ARG, "countTrue: bad argument");
     *count = 0;
-    BoolView m;
-    dn_status st = make_bool_view(m, a, "countTrue");
-    if (st != DN_OK) return st;
-    if (m.n == 0) return DN_OK;
-    merge_bool_view(m);
     void *scratch = nullptr;
-    st = scratch_alloc(sizeof(unsigned long long), &scratch);
+    dn_status st = scratch_alloc(sizeof(unsigned long long), &scratch);
     if (st != DN_OK) return st;
-    DN_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), current_stream()));
-    const uint32_t nblocks = (uint32_t)(((uint64_t)m.n + kIdxThreads * kItems - 1) / (kIdxThreads * kItems));
-    DN_LAUNCH(mask_count_kernel, tiles_grid(nblocks, 16), kIdxThreads, 0, m, (unsigned long long *)scratch);
+    st = count_true_async(a, static_cast<unsigned long long *>(scratch));
     unsigned long long h = 0;
-    cudaError_t e = cudaMemcpyAsync(&h, scratch, sizeof h, cudaMemcpyDeviceToHost, current_stream());
-    if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());
+    cudaError_t e = cudaSuccess;
+    if (st == DN_OK) {
+        e = cudaMemcpyAsync(&h, scratch, sizeof h, cudaMemcpyDeviceToHost, current_stream());
+        if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());
+    }
     scratch_free(scratch);
+    if (st != DN_OK) return st;
     if (e != cudaSuccess) return cuda_error(e, "countTrue");
     *count = (int64_t)h;
     return DN_OK;

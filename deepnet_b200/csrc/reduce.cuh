@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "ew_ops.cuh"
+#include "peer.cuh"
 
 namespace dn {
 
@@ -71,7 +72,18 @@ struct RedParams {
     int64_t part_len;     // elements per part / chunk
     void *partials;       // [nrows][ctas_per_row] states when more than one CTA shares a row
     int32_t ctas_per_row;
+    PeerSync peer;        // sharded launches (shard.cu): every output is also stored into the peers' result buffers
+    char *dst2;           // fused Min/Max + ArgMin/ArgMax: the int64 index target (same ELEMENT strides as dst)
+    int32_t dst2_scale;   // byte offset in dst2 = byte offset in dst * dst2_scale (8 / sizeof(value type))
 };
+
+// The one place an output element is written: the local target and, in a sharded launch, the same offset of every
+// peer's copy of the result (plain stores to peer-mapped memory over NVLink).
+template <class Out>
+__device__ __forceinline__ void red_store(const RedParams &p, char *dst, int64_t toff, Out v) {
+    *reinterpret_cast<Out *>(dst + toff) = v;
+    for (int k = 0; k < p.peer.npeers; ++k) *reinterpret_cast<Out *>(dst + toff + p.peer.delta[k]) = v;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Operators.  State must be trivially copyable.  `ordered` ops get the per-round NaN vote in the rows family.
@@ -239,6 +251,43 @@ struct ArgOp {
 template <class Op> struct IsArgOp : std::false_type {};
 template <class T, bool IsMax> struct IsArgOp<ArgOp<T, IsMax>> : std::true_type {};
 
+// Min/Max AND ArgMin/ArgMax of a float row in one pass: the two folds have different NaN rules (the value fold lets
+// a NaN replace the running value, the arg fold never lets one win), so the state carries both.
+template <class T, bool IsMax>
+struct MinMaxArgOp {
+    using In = T; using Out = T;
+    using V = MinMaxFloatOp<T, IsMax>;
+    using A = ArgOp<T, IsMax>;
+    struct State { T val; int32_t flags; T aval; int64_t idx; };
+    static constexpr bool ordered = true;
+    __device__ static T neutral() { return V::neutral(); }
+    __device__ static bool better(T a, T b) { return V::better(a, b); }
+    __device__ static T pick(T a, T b) { return V::pick(a, b); }
+    __device__ static State identity() {
+        return State{V::neutral(), 0, IsMax ? Limits<T>::lowest() : Limits<T>::max(), (int64_t)DN_NOT_FOUND};
+    }
+    __device__ static void step(State &s, T v, int64_t i) {
+        s.val = better(s.val, v) ? s.val : v;
+        s.flags |= 2 | (v != v ? 1 : 0);
+        if (better(v, s.aval)) { s.aval = v; s.idx = i; }
+    }
+    __device__ static State combine(State a, State b) {
+        const typename V::State v = V::combine(typename V::State{a.val, a.flags}, typename V::State{b.val, b.flags});
+        const typename A::State x = A::combine(typename A::State{a.aval, a.idx}, typename A::State{b.aval, b.idx});
+        return State{v.val, v.flags, x.val, x.idx};
+    }
+    __device__ static Out finalize(State s) { return V::finalize(typename V::State{s.val, s.flags}); }
+};
+template <class Op> struct IsFusedArgOp : std::false_type {};
+template <class T, bool IsMax> struct IsFusedArgOp<MinMaxArgOp<T, IsMax>> : std::true_type {};
+
+// Writes the result(s) of one output element.
+template <class Op>
+__device__ __forceinline__ void red_emit(const RedParams &p, int64_t toff, const typename Op::State &s) {
+    red_store<typename Op::Out>(p, p.dst, toff, Op::finalize(s));
+    if constexpr (IsFusedArgOp<Op>::value) red_store<int64_t>(p, p.dst2, toff * p.dst2_scale, s.idx);
+}
+
 template <class T>
 struct FindOp {
     using In = T; using Out = int64_t; using State = int64_t;
@@ -298,6 +347,15 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
                 if (j < n) probe += v[j];
+            if constexpr (IsFusedArgOp<Op>::value) {  // the arg fold: NaNs never win (strict compare)
+                const int r0 = (int)(i0 - begin);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    if (j < n && Op::better(v[j], st.aval)) {
+                        st.aval = v[j];
+                        ridx = r0 + j;
+                    }
+            }
             if (__any_sync(kFull, probe != probe)) {  // rare
                 int64_t my_nan = -1;
 #pragma unroll
@@ -397,6 +455,12 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
             v = Op::pick(v, o);
         }
         State out;
+        if constexpr (IsFusedArgOp<Op>::value) {
+            typename Op::A::State a{st.aval, ridx >= 0 ? begin + ridx : (int64_t)DN_NOT_FOUND};
+            a = warp_combine_unordered<typename Op::A>(a);
+            out.aval = a.val;
+            out.idx = a.idx;
+        }
         out.flags = (end > begin ? 2 : 0) | (last_nan >= 0 ? 1 : 0);
         out.val = v;
         if (last_nan >= 0 && last_nan == end - 1) out.val = p[last_nan];  // piece ends with the NaN itself
@@ -408,44 +472,58 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
     }
 }
 
+// Register target of the rows kernel: the folds over 4- and 8-byte elements need <= 64 registers and run best at
+// exactly that (4 CTAs per SM: the loads of a group stay in flight; left alone ptxas squeezes them to 48 registers
+// for a fifth CTA and serialises the loads — measured 5-7 % slower on C3). Sub-word types and the fused
+// value+index fold need more and get no hint.
+template <class Op> struct RowsMinBlocks { static constexpr int value = sizeof(typename Op::In) >= 4 ? 4 : 1; };
+template <class T, bool IsMax> struct RowsMinBlocks<MinMaxArgOp<T, IsMax>> { static constexpr int value = 3; };
+
 // parts == 1: warp per row.  parts == 8*S: one CTA per (row, s); its 8 warps take consecutive parts.
 template <class Op>
-__global__ void __launch_bounds__(kRedThreads) reduce_rows_kernel(const __grid_constant__ RedParams p, const Op op) {
+__global__ void __launch_bounds__(kRedThreads, RowsMinBlocks<Op>::value) reduce_rows_kernel(const __grid_constant__ RedParams p, const Op op) {
     using State = typename Op::State;
     using Out = typename Op::Out;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ State sm[kRedWarps];
     if (p.parts == 1) {
         for (uint64_t r = (uint64_t)blockIdx.x * kRedWarps + warp; r < p.nrows; r += (uint64_t)gridDim.x * kRedWarps) {
             int64_t soff, toff;
             red_offsets(p.outer, (uint32_t)r, soff, toff);
             State s = warp_fold_part<Op>(op, p.src + soff, 0, p.len, lane);
-            if (lane == 0) *reinterpret_cast<Out *>(p.dst + toff) = Op::finalize(s);
+            // every lane holds the row's state: lane 0 writes the local target, lanes 1..npeers one peer copy each
+            if (lane <= p.peer.npeers) {
+                const int64_t d = lane == 0 ? 0 : p.peer.delta[lane - 1];
+                *reinterpret_cast<Out *>(p.dst + toff + d) = Op::finalize(s);
+                if constexpr (IsFusedArgOp<Op>::value)
+                    *reinterpret_cast<int64_t *>(p.dst2 + toff * p.dst2_scale + d) = s.idx;
+            }
         }
-        return;
-    }
-    __shared__ State sm[kRedWarps];
-    const uint64_t total = (uint64_t)p.nrows * p.ctas_per_row;
-    for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
-        const uint32_t r = (uint32_t)(w / p.ctas_per_row);
-        const int s_idx = (int)(w % p.ctas_per_row);
-        int64_t soff, toff;
-        red_offsets(p.outer, r, soff, toff);
-        const int64_t part = (int64_t)s_idx * kRedWarps + warp;
-        int64_t b = part * p.part_len, e = b + p.part_len;
-        if (b > p.len) b = p.len;
-        if (e > p.len) e = p.len;
-        State s = warp_fold_part<Op>(op, p.src + soff, b, e, lane);
-        if (lane == 0) sm[warp] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            State acc = sm[0];
+    } else {
+        const uint64_t total = (uint64_t)p.nrows * p.ctas_per_row;
+        for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
+            const uint32_t r = (uint32_t)(w / p.ctas_per_row);
+            const int s_idx = (int)(w % p.ctas_per_row);
+            int64_t soff, toff;
+            red_offsets(p.outer, r, soff, toff);
+            const int64_t part = (int64_t)s_idx * kRedWarps + warp;
+            int64_t b = part * p.part_len, e = b + p.part_len;
+            if (b > p.len) b = p.len;
+            if (e > p.len) e = p.len;
+            State s = warp_fold_part<Op>(op, p.src + soff, b, e, lane);
+            if (lane == 0) sm[warp] = s;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                State acc = sm[0];
 #pragma unroll
-            for (int k = 1; k < kRedWarps; ++k) acc = Op::combine(acc, sm[k]);
-            if (p.ctas_per_row == 1) *reinterpret_cast<Out *>(p.dst + toff) = Op::finalize(acc);
-            else reinterpret_cast<State *>(p.partials)[(uint64_t)r * p.ctas_per_row + s_idx] = acc;
+                for (int k = 1; k < kRedWarps; ++k) acc = Op::combine(acc, sm[k]);
+                if (p.ctas_per_row == 1) red_emit<Op>(p, toff, acc);
+                else reinterpret_cast<State *>(p.partials)[(uint64_t)r * p.ctas_per_row + s_idx] = acc;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
+    peer_exit(p.peer);
 }
 
 // Ordered combine of the per-CTA partial states of each row; one thread per row.
@@ -454,13 +532,15 @@ __global__ void __launch_bounds__(kRedThreads) reduce_finalize_kernel(const __gr
     using State = typename Op::State;
     using Out = typename Op::Out;
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.nrows) return;
-    const State *part = reinterpret_cast<const State *>(p.partials) + r * p.ctas_per_row;
-    State acc = part[0];
-    for (int k = 1; k < p.ctas_per_row; ++k) acc = Op::combine(acc, part[k]);
-    int64_t soff, toff;
-    red_offsets(p.outer, (uint32_t)r, soff, toff);
-    *reinterpret_cast<Out *>(p.dst + toff) = Op::finalize(acc);
+    if (r < p.nrows) {
+        const State *part = reinterpret_cast<const State *>(p.partials) + r * p.ctas_per_row;
+        State acc = part[0];
+        for (int k = 1; k < p.ctas_per_row; ++k) acc = Op::combine(acc, part[k]);
+        int64_t soff, toff;
+        red_offsets(p.outer, (uint32_t)r, soff, toff);
+        red_emit<Op>(p, toff, acc);
+    }
+    peer_exit(p.peer);
 }
 
 // The same for rows shared by MANY CTAs (whole-tensor folds: up to 1024 partials per row): one warp per row, lane l
@@ -472,28 +552,30 @@ __global__ void __launch_bounds__(kRedThreads) reduce_finalize_warp_kernel(const
     using Out = typename Op::Out;
     const int lane = threadIdx.x & 31;
     const uint64_t r = (uint64_t)blockIdx.x * kRedWarps + (threadIdx.x >> 5);
-    if (r >= p.nrows) return;
-    const State *part = reinterpret_cast<const State *>(p.partials) + r * p.ctas_per_row;
-    const int per = (p.ctas_per_row + 31) / 32;
-    const int b = lane * per;
-    int e = b + per;
-    if (e > p.ctas_per_row) e = p.ctas_per_row;
-    State acc = Op::identity();
-    bool any = false;
-    for (int k = b; k < e; ++k) {
-        const State v = part[k];
-        acc = any ? Op::combine(acc, v) : v;
-        any = true;
+    if (r < p.nrows) {  // warp-uniform
+        const State *part = reinterpret_cast<const State *>(p.partials) + r * p.ctas_per_row;
+        const int per = (p.ctas_per_row + 31) / 32;
+        const int b = lane * per;
+        int e = b + per;
+        if (e > p.ctas_per_row) e = p.ctas_per_row;
+        State acc = Op::identity();
+        bool any = false;
+        for (int k = b; k < e; ++k) {
+            const State v = part[k];
+            acc = any ? Op::combine(acc, v) : v;
+            any = true;
+        }
+        // ordered combine over the lanes that hold something (lane order == partial order)
+        State total = shfl_idx_any(acc, 0);
+        const int used = (p.ctas_per_row + per - 1) / per;
+        for (int l = 1; l < used; ++l) total = Op::combine(total, shfl_idx_any(acc, l));
+        if (lane == 0) {
+            int64_t soff, toff;
+            red_offsets(p.outer, (uint32_t)r, soff, toff);
+            red_emit<Op>(p, toff, total);
+        }
     }
-    // ordered combine over the lanes that hold something (lane order == partial order)
-    State total = shfl_idx_any(acc, 0);
-    const int used = (p.ctas_per_row + per - 1) / per;
-    for (int l = 1; l < used; ++l) total = Op::combine(total, shfl_idx_any(acc, l));
-    if (lane == 0) {
-        int64_t soff, toff;
-        red_offsets(p.outer, (uint32_t)r, soff, toff);
-        *reinterpret_cast<Out *>(p.dst + toff) = Op::finalize(total);
-    }
+    peer_exit(p.peer);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -541,21 +623,25 @@ __global__ void __launch_bounds__(kRedThreads) reduce_cols_kernel(const __grid_c
             for (int j = 0; j < VEC; ++j) op_step(op, st[j], v.v[j], i);
         }
     }
+    bool writer = active;
     if (blockDim.y > 1) {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) sm[(threadIdx.y * blockDim.x + threadIdx.x) * VEC + j] = st[j];
         __syncthreads();
-        if (threadIdx.y != 0) return;
-        for (int y = 1; y < (int)blockDim.y; ++y)
+        writer = active && threadIdx.y == 0;
+        if (writer)
+            for (int y = 1; y < (int)blockDim.y; ++y)
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) st[j] = Op::combine(st[j], sm[(y * blockDim.x + threadIdx.x) * VEC + j]);
+                for (int j = 0; j < VEC; ++j) st[j] = Op::combine(st[j], sm[(y * blockDim.x + threadIdx.x) * VEC + j]);
     }
-    if (!active) return;
+    if (writer) {
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        if (gridDim.y == 1) *reinterpret_cast<Out *>(p.dst + toff + j * p.outer.tstride[0]) = Op::finalize(st[j]);
-        else reinterpret_cast<State *>(p.partials)[(o0 + j) * gridDim.y + blockIdx.y] = st[j];
+        for (int j = 0; j < VEC; ++j) {
+            if (gridDim.y == 1) red_emit<Op>(p, toff + j * p.outer.tstride[0], st[j]);
+            else reinterpret_cast<State *>(p.partials)[(o0 + j) * gridDim.y + blockIdx.y] = st[j];
+        }
     }
+    peer_exit(p.peer);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -569,6 +655,7 @@ struct RedPlan {
     int64_t oshape[DN_MAX_DIMS], ostride_s[DN_MAX_DIMS], ostride_t[DN_MAX_DIMS];  // elements, innermost-first
     int64_t nrows;
     int in_size, out_size;
+    char *dst2 = nullptr;  // fused Min/Max + Arg only
 };
 
 // Validates shapes (a: [..., L], t: [...]) and canonicalises the outer dims (drop size-1, sort by source stride,
@@ -601,6 +688,13 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
         p.partials = nullptr;
         p.ctas_per_row = 1;
         void *scratch = nullptr;
+        // sharded launch (shard.cu): the kernel that STORES the outputs also stores them into the peers' buffers
+        // and runs the exit barrier; a kernel that only produces partials runs plain
+        PeerSync sync = {};
+        peer_take(sync);
+        p.peer = PeerSync{};
+        p.dst2 = plan.dst2;
+        p.dst2_scale = plan.in_size ? 8 / plan.in_size : 1;
         if (rows_family) {
             const int64_t warps_wanted = (int64_t)sms * 32;  // enough resident warps to cover HBM latency
             const int64_t bytes = L * plan.in_size;
@@ -619,6 +713,7 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
                 int64_t ctas = (rc + kRedWarps - 1) / kRedWarps;
                 const int64_t cap = (int64_t)sms * 16;
                 if (ctas > cap) ctas = cap;
+                p.peer = sync;
                 DN_LAUNCH((reduce_rows_kernel<Op>), (unsigned)ctas, kRedThreads, 0, p, op);
             } else {
                 // S CTAs per row so that rc*S CTAs fill the machine; every part stays >= 4 KiB
@@ -642,7 +737,9 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
                 int64_t ctas = rc * S;
                 const int64_t cap = (int64_t)sms * 16;
                 if (ctas > cap) ctas = cap;
+                if (S == 1) p.peer = sync;
                 DN_LAUNCH((reduce_rows_kernel<Op>), (unsigned)ctas, kRedThreads, 0, p, op);
+                p.peer = sync;
                 if (S >= 32) {
                     DN_LAUNCH((reduce_finalize_warp_kernel<Op>), (unsigned)((rc + kRedWarps - 1) / kRedWarps), kRedThreads, 0, p);
                 } else if (S > 1) {
@@ -680,11 +777,13 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
                 p.partials = scratch;
             }
             const size_t smem = ty > 1 ? (size_t)tx * ty * sizeof(State) * vec : 0;
+            if (gy == 1) p.peer = sync;
             if (vec > 1)
                 DN_LAUNCH((reduce_cols_kernel<Op, kColsVec>), dim3((unsigned)gx, (unsigned)gy), dim3(tx, ty), smem, p, op);
             else
                 DN_LAUNCH((reduce_cols_kernel<Op, 1>), dim3((unsigned)gx, (unsigned)gy), dim3(tx, ty), smem, p, op);
             if (gy > 1) {
+                p.peer = sync;
                 DN_LAUNCH((reduce_finalize_kernel<Op>), (unsigned)((rc + kRedThreads - 1) / kRedThreads),
                           kRedThreads, 0, p);
             }

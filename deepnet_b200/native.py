@@ -129,6 +129,12 @@ _DEVICE_SIGNATURES = {
     "poll_index_error": [C.POINTER(C.c_int32)],
     "alloc": [C.c_int64, C.POINTER(C.c_void_p)],
     "free": [C.c_void_p],
+    "free_deferred": [C.c_void_p],
+    "release_stream": [C.c_void_p],
+    "host_register": [C.c_void_p, C.c_int64],
+    "host_unregister": [C.c_void_p],
+    "transfer_h2d": [_P, _P],
+    "transfer_d2h": [_P, _P],
     "alloc_host": [C.c_int64, C.POINTER(C.c_void_p)],
     "free_host": [C.c_void_p],
     "memset_zero": [C.c_void_p, C.c_int64],
@@ -143,7 +149,31 @@ _DEVICE_SIGNATURES = {
     "get_item": [_P, C.POINTER(C.c_int64), C.c_void_p],
     "set_item": [_P, C.POINTER(C.c_int64), C.c_void_p],
     "arg_reduce_combine": [C.c_int32, _P, _P, _P],
+    # leading-axis sharding (include/dn_tensor.h "Multi-GPU")
+    "shard_group_create": [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64,
+                           C.POINTER(C.c_void_p)],
+    "shard_group_handle": [C.c_void_p, C.c_int32, C.c_void_p],
+    "shard_group_connect": [C.c_void_p, C.c_void_p],
+    "shard_group_destroy": [C.c_void_p],
+    "shard_set_stream": [C.c_void_p, C.c_int32, C.c_void_p],
+    "shard_sync": [C.c_void_p, C.c_int32],
+    "shard_slab": [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+    "shard_heap_alloc": [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)],
+    "shard_heap_reset": [C.c_void_p, C.c_int32],
+    "shard_barrier": [C.c_void_p, C.c_int32],
+    "shard_reduce_last_axis": [C.c_void_p, C.c_int32, C.c_int32, _P, C.c_int64, _P],
+    "shard_arg_reduce_last_axis": [C.c_void_p, C.c_int32, C.c_int32, _P, C.c_int64, _P],
+    "shard_find_last_axis": [C.c_void_p, C.c_int32, C.c_void_p, _P, C.c_int64, _P],
+    "shard_minmax_arg_last_axis": [C.c_void_p, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P],
+    "shard_reduce_sharded_axis": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, _P, C.c_int64, _P],
+    "shard_all_gather_rows": [C.c_void_p, C.c_int32, _P, C.c_int64, C.c_int64],
+    "shard_count_true": [C.c_void_p, C.c_int32, _P, C.POINTER(C.c_int64)],
+    "shard_count_true_begin": [C.c_void_p, C.c_int32, _P],
+    "shard_count_true_end": [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)],
+    "shard_true_indices": [C.c_void_p, C.c_int32, _P, C.c_int64, C.c_int64, _P, C.c_int64],
+    "shard_masked_get": [C.c_void_p, C.c_int32, _P, C.c_int64, C.c_int64, _P, _P],
 }
+DN_SHARD_MAX_RANKS, DN_SHARD_HANDLE_BYTES = 8, 64
 
 ALL_PRODUCT_SYMBOLS = (
     ["dn_" + n for n in _OPERATOR_SIGNATURES] + ["dn_" + n for n in _DEVICE_SIGNATURES] +

@@ -104,6 +104,9 @@ dn_status dn_get_device(int32_t *device);
  * NULL = the default stream. */
 dn_status dn_set_stream(void *stream);
 dn_status dn_get_stream(void **stream);
+/* Tells the library that `stream` is about to be destroyed: it is dropped from the device's list of streams that
+ * storage releases are ordered after (dn_free / dn_free_deferred). */
+dn_status dn_release_stream(void *stream);
 /* cuCtxSynchronize on the calling thread's stream (Benchmark.fs:211-213 calls this after every op). */
 dn_status dn_sync(void);
 /* Cfg.Stacktrace (CudaCfg.fs:33-35): when non-zero, gather/scatter synchronise and return
@@ -123,9 +126,21 @@ const char *dn_version(void);
  * thread's stream, so a storage may be freed right after the last op that uses it was enqueued.
  * ------------------------------------------------------------------------------------------------------------- */
 dn_status dn_alloc(int64_t nbytes, void **ptr);          /* nbytes <= 0 allocates 1 byte (CudaBackend.fs:56-58) */
+/* Stream-ordered on the calling thread's stream; if the library knows other streams on the device (dn_set_stream),
+ * the release is additionally ordered after everything they hold. */
 dn_status dn_free(void *ptr);
-dn_status dn_alloc_host(int64_t nbytes, void **ptr);     /* pinned host memory (CudaRegMem.fs:123-146)          */
+/* Release from a thread that owns no stream on the storage's device — a .NET finalizer thread (the reference frees
+ * from the finalizer, CudaBackend.fs:73-74), a destructor run by a collector thread. Any device, any thread, never
+ * touches a stream: the pointer is queued on its device and released by the next dn_alloc / dn_sync issued by a
+ * thread working on that device, behind a fence over all streams the library knows there. */
+dn_status dn_free_deferred(void *ptr);
+dn_status dn_alloc_host(int64_t nbytes, void **ptr);     /* pinned host memory                                   */
 dn_status dn_free_host(void *ptr);
+/* CudaRegMem.register / unregister (CudaRegMem.fs:114-146): page-locks EXISTING host memory (a pinned managed
+ * array) so that transfers from / to it are asynchronous DMA. DN_ERR_INVALID_ARG when the range cannot be registered
+ * (the reference's CannotCudaRegisterMemoryException: the caller falls back to plain pinning). */
+dn_status dn_host_register(void *ptr, int64_t nbytes);
+dn_status dn_host_unregister(void *ptr);
 dn_status dn_memset_zero(void *ptr, int64_t nbytes);
 /* Transfer (CudaBackend.fs:206-270) for C-contiguous blocks; async on the stream when the host side is pinned. */
 dn_status dn_memcpy_h2d(void *dst_dev, const void *src_host, int64_t nbytes);
@@ -134,6 +149,13 @@ dn_status dn_memcpy_d2d(void *dst_dev, const void *src_dev, int64_t nbytes);
 /* Same as dn_memcpy_d2h but does not wait: the host buffer (pinned) is valid after dn_sync() on the same stream.
  * This is the `Cfg.Stream <> NullStream` branch of Transfer (CudaBackend.fs:243-247, AsyncCopyFromDevice). */
 dn_status dn_memcpy_d2h_async(void *dst_host, const void *src_dev, int64_t nbytes);
+/* ITensorBackend.Transfer (TensorBackend.fs:68; CudaBackend.fs:206-270) for ARBITRARY views of equal shape and type:
+ * host_t->base is a host pointer, dev_t->base a device pointer. C-contiguous pairs are one DMA; any other layout is
+ * handled natively (strided pack / unpack of the host view through pinned staging, layout change on the device with
+ * the strided copy kernel), where the reference copies on the host and through a temporary device tensor.
+ * h2d is ordered on the calling thread's stream; d2h blocks until the host view holds the data. */
+dn_status dn_transfer_h2d(const dn_tensor *dev_t, const dn_tensor *host_t);
+dn_status dn_transfer_d2h(const dn_tensor *host_t, const dn_tensor *dev_t);
 /* Stream ordering helpers for callers that overlap transfers with compute on several streams: record an event on
  * the calling thread's stream / make the calling thread's stream wait for it. Events are created by dn_event_create
  * and are opaque. */
@@ -240,10 +262,93 @@ dn_status dn_batched_mat_mat_dot(const dn_tensor *t, const dn_tensor *a, const d
 dn_status dn_batched_invert(const dn_tensor *t, const dn_tensor *a);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Multi-GPU combine steps for leading-axis sharding (new; the reference has no multi-GPU path — SURVEY.md §8e).
- * The bulk tensors never move: every rank reduces its slab with the operators above; these entry points only
- * fold the per-rank partial results that the host has gathered (torch.distributed / NCCL all_gather).
+ * Multi-GPU: leading-axis sharding over the GPUs of one box (new; the reference is single device —
+ * Tensor/Tensor/Cuda/CudaUtils.fs:42-46 creates one context; SURVEY.md §8e defines the partitioning).
+ *
+ * Every rank owns a contiguous slab of dim 0 of every operand; element-wise operators need no communication and
+ * are the ordinary entry points above on each device. A *shard group* connects the ranks for the operators whose
+ * result every rank needs in full (reductions, arg-reductions, Find, TrueIndices, MaskedGet):
+ *   - every rank owns a WINDOW of device memory that all other ranks can address (NVLink / NVSwitch peer access
+ *     inside one process, CUDA IPC mappings between processes); full results live in its symmetric heap
+ *     (dn_shard_heap_alloc: the same sequence of allocations on every rank yields the same window offsets);
+ *   - a sharded operator is ONE kernel launch per rank: the reduction kernel stores each output row into the local
+ *     result AND the same offset of every peer's result, and its last CTA publishes the rank's epoch into every
+ *     rank's flag array; the launch is followed by stream memory operations (cuStreamWaitValue32) that hold the
+ *     rank's stream until every rank has published, so later work on the stream sees the complete replicated
+ *     result. No NCCL launch is involved, no kernel spins, the bulk tensors never move.
+ * Process models: (a) one process driving all devices (the F# host: nlocal == world), (b) one process per GPU
+ * (torchrun: nlocal == 1; the 64-byte window handles are exchanged by the host through any side channel).
+ * Ranks may share a device (tests on a single GPU). Calls on one rank must come from one thread at a time and are
+ * COLLECTIVE: every rank issues the same sequence of dn_shard_* operator calls. A result buffer may be reused as
+ * the target of a later collective only after at least one other collective (or dn_shard_barrier) in between.
+ * All dn_shard_* calls run on the rank's stream (dn_shard_set_stream; default: a stream owned by the group) and
+ * leave the calling thread's current device and stream unchanged.
  * ------------------------------------------------------------------------------------------------------------- */
+#define DN_SHARD_MAX_RANKS 8
+#define DN_SHARD_HANDLE_BYTES 64
+/* Creates the group object and the windows of the `nlocal` ranks this process drives (local_ranks[i] runs on CUDA
+ * device local_devices[i]); heap_bytes = size of each rank's symmetric heap. */
+dn_status dn_shard_group_create(int32_t world, int32_t nlocal, const int32_t *local_ranks,
+                                const int32_t *local_devices, int64_t heap_bytes, void **group);
+/* The window handle of a LOCAL rank (DN_SHARD_HANDLE_BYTES bytes), to be sent to the other processes. */
+dn_status dn_shard_group_handle(void *group, int32_t rank, void *handle);
+/* Maps the windows of the non-local ranks (handles: world x DN_SHARD_HANDLE_BYTES, entries of local ranks are
+ * ignored; may be NULL when every rank is local) and enables peer access between the devices. */
+dn_status dn_shard_group_connect(void *group, const void *handles);
+dn_status dn_shard_group_destroy(void *group);
+dn_status dn_shard_set_stream(void *group, int32_t rank, void *stream);
+dn_status dn_shard_sync(void *group, int32_t rank);          /* waits for the rank's stream */
+/* Contiguous slab [begin, begin+count) of `nrows` rows owned by `rank`; the remainder goes to the first ranks. */
+dn_status dn_shard_slab(int64_t nrows, int32_t rank, int32_t world, int64_t *begin, int64_t *count);
+/* Symmetric heap: a bump allocator (256-byte granules); reset frees everything. Collective by convention. */
+dn_status dn_shard_heap_alloc(void *group, int32_t rank, int64_t nbytes, void **ptr);
+dn_status dn_shard_heap_reset(void *group, int32_t rank);
+/* Flag barrier over peer memory on the ranks' streams (one tiny kernel per rank). */
+dn_status dn_shard_barrier(void *group, int32_t rank);
+
+/* Reductions over an axis OTHER than the sharded one (every output row lives on one rank). a_local: this rank's
+ * slab [rows_local, ..., L]; t_full: the FULL result [rows_total, ...] in the symmetric heap; the rank computes rows
+ * [row_begin, row_begin + rows_local) and stores them into every rank's t_full. Semantics of dn_reduce_last_axis /
+ * dn_arg_reduce_last_axis / dn_find_last_axis. */
+dn_status dn_shard_reduce_last_axis(void *group, int32_t rank, int32_t op, const dn_tensor *t_full,
+                                    int64_t row_begin, const dn_tensor *a_local);
+dn_status dn_shard_arg_reduce_last_axis(void *group, int32_t rank, int32_t op, const dn_tensor *t_full,
+                                        int64_t row_begin, const dn_tensor *a_local);
+dn_status dn_shard_find_last_axis(void *group, int32_t rank, const void *value, const dn_tensor *t_full,
+                                  int64_t row_begin, const dn_tensor *a_local);
+/* Min/Max AND ArgMin/ArgMax of the same source in ONE pass over it (op: dn_arg_reduce_op; float32 / float64):
+ * t_val_full receives exactly what MinLastAxis / MaxLastAxis would, t_idx_full what ArgMin / ArgMaxLastAxis would.
+ * group == NULL: plain single-device call (row_begin must be 0). */
+dn_status dn_shard_minmax_arg_last_axis(void *group, int32_t rank, int32_t op, const dn_tensor *t_val_full,
+                                        const dn_tensor *t_idx_full, int64_t row_begin, const dn_tensor *a_local);
+/* Reductions over the SHARDED axis (includes whole-tensor folds of a flattened slab). a_local: [..., n_local] with
+ * the sharded axis last (the frontend's axis->last permutation), holding global positions [axis_begin,
+ * axis_begin + n_local); t: [...] anywhere in device memory, receives the full result on every rank. Per-rank
+ * partials are stored into every rank's window and folded locally IN RANK ORDER, so the result is identical on
+ * every rank: float Min/Max keep the host's order-dependent NaN rule, ArgMin/ArgMax first-occurrence semantics
+ * through (value, global index) pairs, Find the lowest global index. kind: 0 = dn_reduce_op, 1 = dn_arg_reduce_op,
+ * 2 = Find (`value` points to one element of a's dtype). */
+dn_status dn_shard_reduce_sharded_axis(void *group, int32_t rank, int32_t kind, int32_t op, const void *value,
+                                       const dn_tensor *t, int64_t axis_begin, const dn_tensor *a_local);
+/* All-gather of row blocks already present in the local t_full (symmetric heap): rows [row_begin, row_begin+nrows)
+ * of the C-contiguous t_full are stored into every rank's t_full. nrows may differ between ranks (ragged). */
+dn_status dn_shard_all_gather_rows(void *group, int32_t rank, const dn_tensor *t_full, int64_t row_begin,
+                                   int64_t nrows);
+/* countTrue of the local mask slab, exchanged: counts[r] = number of true elements on rank r. Blocking (the
+ * frontend needs the total before it can allocate the result, Tensor.fs:2259-2262,3025). A single thread that drives
+ * several ranks issues _begin on every rank first, then _end on every rank. */
+dn_status dn_shard_count_true(void *group, int32_t rank, const dn_tensor *mask_local, int64_t *counts);
+dn_status dn_shard_count_true_begin(void *group, int32_t rank, const dn_tensor *mask_local);
+dn_status dn_shard_count_true_end(void *group, int32_t rank, int64_t *counts);
+/* TrueIndices of a bool tensor sharded along dim 0: local compaction into rows [row_offset, row_offset + nrows_local)
+ * of t_full [nTrue_total, ndims] with dim-0 coordinates shifted by dim0_begin, blocks replicated in rank order
+ * (= the logical row-major order of the full tensor, ScalarOps.fs:699-707). */
+dn_status dn_shard_true_indices(void *group, int32_t rank, const dn_tensor *t_full, int64_t row_offset,
+                                int64_t nrows_local, const dn_tensor *mask_local, int64_t dim0_begin);
+/* MaskedGet with a full-shape mask, both sharded along dim 0 (ScalarOps.fs:667-681): t_full is 1-D [nTrue_total]. */
+dn_status dn_shard_masked_get(void *group, int32_t rank, const dn_tensor *t_full, int64_t elem_offset,
+                              int64_t nelems_local, const dn_tensor *a_local, const dn_tensor *mask_local);
+
 /* Fold `nparts` partial (value, index) pairs per output into t (DN_I64): best value wins, lowest global index on
  * ties, DN_NOT_FOUND partials never win. vals: [nparts, n] of a's dtype, idxs: [nparts, n] DN_I64 (global indices). */
 dn_status dn_arg_reduce_combine(int32_t op, const dn_tensor *t, const dn_tensor *vals, const dn_tensor *idxs);

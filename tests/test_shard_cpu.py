@@ -1,5 +1,6 @@
 """Leading-axis sharding over 2 ranks with the `gloo` backend on CPU (the compute device is the HostTensor oracle,
-so this exercises only the host-side sharding / combine logic of deepnet_b200/shard.py): sharded results must equal
+so this exercises the sharding / ordered-combine ALGORITHM restated in oracle/shard_gloo.py; the product path — the
+dn_shard_* entry points over peer memory — is covered by tests/test_shard_gpu.py against the same oracle): sharded results must equal
 the unsharded ones bit for bit for integer / index results, and for float Min/Max including the NaN rules."""
 import os
 import socket
@@ -28,7 +29,7 @@ def _worker(rank, world, port, out_dir):
     try:
         from deepnet_b200 import NotFound, Tensor, dtypes
         from deepnet_b200 import layout as TL
-        from deepnet_b200.shard import LeadingAxisSharding, slab
+        from oracle.shard_gloo import LeadingAxisSharding, slab
         from oracle.host_tensor import HostTensor, TensorHostStorage
 
         def wrap(t: torch.Tensor) -> Tensor:
@@ -110,7 +111,7 @@ def test_sharded_reductions_two_ranks_gloo(tmp_path):
 
 
 def test_slab_partition():
-    from deepnet_b200.shard import slab
+    from oracle.shard_gloo import slab
     for n in (0, 1, 7, 8, 101, 16384):
         for w in (1, 2, 4, 8):
             parts = [slab(n, r, w) for r in range(w)]
