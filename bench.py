@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200 Tensor backend (contract: see the task brief / DESIGN.md §Measurement).
+"""bench.py — headline benchmark of the B200 Tensor backend (contract: see the task brief / DESIGN.md §5).
 
 Metric (BASELINE.json): element-wise / reduction HBM GB/s (% of B200 peak) at 1/2/4/8 GPUs vs HostTensor.
 Workload (BASELINE.json configs[1], SURVEY.md §8d "C2"): strided / broadcast element-wise operators on transposed,
 broadcast, sliced and reversed views of [16384, 16384] tensors (2^28 elements) in float32, float64 and int32.
-One "step" = one pass over that whole case list (33 backend calls). `value` = algorithmic bytes of the step,
-summed over all ranks, divided by the step time (max over ranks) — inputs resident in HBM. `e2e` = the same case
-list driven through the public API from PINNED HOST buffers: every step copies the inputs host->device, runs the
-calls, and copies one result per dtype back.
+One "step" = one pass over that whole case list (33 backend calls).
 
-Multi-GPU (`--gpus N`, launched under torchrun): the leading axis is sharded, every rank owns one [16384, 16384]
-slab of every operand (weak scaling); element-wise operators need no collective.
+`value`  = algorithmic bytes of the step, summed over all ranks, / step time (max over ranks), inputs resident in HBM.
+`e2e`    = the same case list through the public API from PINNED HOST buffers: every step uploads the inputs
+           (dn_memcpy_h2d), runs the 33 calls and downloads the final result of every dtype (the target of the last
+           call) and the bool mask; uploads, kernels and downloads overlap on three streams.
+Multi-GPU (`--gpus N`, one process per GPU under torchrun): STRONG scaling — the 2^28-element tensors are split along
+the leading axis into N equal slabs; a rank holds its slab of every operand AS VIEWED (for
+`a.T + b` that is the column block a[:, r0:r1], stored [16384, rows] and used through its transposed view).
+Element-wise operators need no collective. A weak-scaling line (one full-size tensor set per rank) is reported beside it.
+`sharded_reductions` = BASELINE.json configs[2]: ArgMax + Max over 262144 x 1000 float32 split over the ranks
+(strong scaling) through the dn_shard_* entry points — peer-memory stores + flag barrier, no NCCL on the path.
+
+Every number is checked: after the timed region the timed buffers are compared with the HostTensor oracle
+(`"verified"`; `--verify` re-runs and checks all 33 calls).
 
 `--impl reference` times the reference's own CPU path for the same case list — the C++ restatement of HostTensor
-in oracle/ (the F# original cannot run in this image: no dotnet), with its threading policy, on the host cores
+in oracle/ (the F# original cannot run in this image: no dotnet), with its threading policy, on all host cores
 of this box, on a bounded sample ([8192,8192] tensors, 30.5 GB algorithmic per step).
 """
 from __future__ import annotations
@@ -33,9 +41,17 @@ if ROOT not in sys.path:
 
 import numpy as np
 
-NCU_F64_ADD_TRAFFIC = 4.294980e9 + 2.118896e9  # profiles/r01c_ew_add_contig256_f64.raw.csv
 METRIC = "elementwise/reduction HBM GB/s (% of B200 peak) at 1/2/4/8 GPUs vs HostTensor"
 SIDE = 16384  # 2^28 elements per tensor
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch on the contiguous [16384,16384] case, from the committed
+# `ncu --set full` captures (file named per entry); None for kernels without a capture.
+NCU_TRAFFIC = {
+    "ew_kernel<BinaryF<float,ADD>,VEC=8> (256-bit vector kernel)": (2.147553e9 + 1.041274e9, "profiles/r01b_ew_add_contig256.raw.csv"),
+    "ew_kernel<BinaryF<double,ADD>,VEC=4> (256-bit vector kernel)": (4.294980e9 + 2.118896e9, "profiles/r01c_ew_add_contig256_f64.raw.csv"),
+    "ew_xpose_kernel<BinaryF<float,ADD>> (register transpose)": (2.147507e9 + 1.039083e9, "profiles/r01_ew_xpose_addT.raw.csv"),
+    "ew_xpose_kernel<BinaryF<double,ADD>> (register transpose)": (4.295036e9 + 2.110988e9, "profiles/r01_ew_xpose_f64_addT.raw.csv"),
+}
 
 
 def load_peaks():
@@ -47,19 +63,22 @@ def load_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# The C2 case list, written once against the frontend so that the CUDA arm, the e2e arm and the CPU arm run the
-# same calls. Each entry: (name, algorithmic bytes, callable).  Algorithmic bytes: every DISTINCT element touched
-# counts once; broadcast operands count their own size.
+# The C2 case list, written once against the frontend so that the CUDA arm, the e2e arm, the verification and the
+# CPU arm run the same calls. Each entry: (name, algorithmic bytes, callable, kernel tag). Algorithmic bytes: every
+# DISTINCT element touched counts once; broadcast operands count their own size.
 # ---------------------------------------------------------------------------------------------------------------
-def build_cases(T, dt, a, b, c, row, col, mask, has_sin: bool):
-    """a, b, c: [R, C]; row: [1, C]; col: [R, 1]; mask: bool [R, C]. Returns the case list for one dtype."""
+def build_cases(T, dt, a, b, c, row, col, mask, has_sin: bool, aT=None, bT=None):
+    """a, b, c: [R, C]; row: [1, C]; col: [R, 1]; mask: bool [R, C]; aT, bT: [R, C] transposed views (default: a.T,
+    b.T — on a leading-axis shard they are views of the rank's column blocks). Returns the case list of one dtype."""
     from deepnet_b200 import dtypes
     s = dtypes.itemsize(dt)
-    R, C = a.Shape
+    R, C = c.Shape
     N = R * C
     nm = dtypes.NAMES[dt]
+    aT = a.T if aT is None else aT
+    bT = b.T if bT is None else bT
     cs, as_, bs = c[1:, 1:], a[1:, 1:], b[1:, 1:]
-    ar0, ar1, aT = a.reverseAxis(0), a.reverseAxis(1), a.T
+    ar0, ar1 = a.reverseAxis(0), a.reverseAxis(1)
     T_ = {"single": "float", "double": "double", "int32": "int"}[nm]
     k_add = f"ew_kernel<BinaryF<{T_},ADD>,VEC={32 // s}> (256-bit vector kernel)"
     k_addT = f"ew_xpose_kernel<BinaryF<{T_},ADD>> (register transpose)"
@@ -74,7 +93,7 @@ def build_cases(T, dt, a, b, c, row, col, mask, has_sin: bool):
         (f"{nm} add reverseAxis0(a) + b", 3 * N * s, lambda: c.FillAdd(ar0, b), k_add),
         (f"{nm} add reverseAxis1(a) + b", 3 * N * s, lambda: c.FillAdd(ar1, b), k_add),
         (f"{nm} copy a.T", 2 * N * s, lambda: c.CopyFrom(aT), f"ew_xpose_kernel<CopyF<{8 * s}-bit>>"),
-        (f"{nm} less a < b.T -> bool", (2 * s + 1) * N, lambda: mask.FillLess(a, b.T), f"ew_xpose_kernel<CompareF<{T_},LESS>>"),
+        (f"{nm} less a < b.T -> bool", (2 * s + 1) * N, lambda: mask.FillLess(a, bT), f"ew_xpose_kernel<CompareF<{T_},LESS>>"),
         (f"{nm} ifThenElse(mask, a, b)", (3 * s + 1) * N, lambda: c.FillIfThenElse(mask, a, b), f"ew_kernel<SelectF<{8 * s}-bit>>"),
     ]
     return cases
@@ -87,12 +106,14 @@ def dtype_list():
     return [(dtypes.DN_F32, np.float32, True), (dtypes.DN_F64, np.float64, False), (dtypes.DN_I32, np.int32, False)]
 
 
-def host_inputs(rng, side, npdt):
+def host_inputs(rng, side, npdt, rows=None):
+    """a, b: [rows, side]; row: [1, side]; col: [rows, 1] — uniform [-50, 50), ints rounded (Benchmark.fs:105-107)."""
+    rows = side if rows is None else rows
     if np.issubdtype(npdt, np.floating):
         mk = lambda shape: rng.uniform(-50, 50, size=shape).astype(npdt)
     else:
         mk = lambda shape: np.rint(rng.uniform(-50, 50, size=shape)).astype(npdt)
-    return mk((side, side)), mk((side, side)), mk((1, side)), mk((side, 1))
+    return mk((rows, side)), mk((rows, side)), mk((1, side)), mk((rows, 1))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -160,11 +181,30 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (HostTensor restatement) on a bounded sample
+# CPU arm: the oracle (HostTensor restatement) on a bounded sample, on ALL host cores whatever launched us
+# (torchrun exports OMP_NUM_THREADS=1)
 # ---------------------------------------------------------------------------------------------------------------
+def use_all_host_cores() -> int:
+    from oracle import host_tensor
+    lib = host_tensor.api().lib
+    lib.dno_set_num_threads.argtypes = [__import__("ctypes").c_int]
+    lib.dno_get_num_threads.restype = __import__("ctypes").c_int
+    lib.dno_set_num_threads(os.cpu_count() or 1)
+    return int(lib.dno_get_num_threads())
+
+
+def host_of(arr: np.ndarray):
+    """HostTensor (oracle device) over `arr` without copying it."""
+    from deepnet_b200 import Tensor
+    from deepnet_b200 import layout as TL
+    from oracle.host_tensor import HostTensor, TensorHostStorage
+    return Tensor(TL.newC(arr.shape), TensorHostStorage(arr.reshape(-1), HostTensor.Dev))
+
+
 def run_cpu_cases(side: int, steps: int, warmup: int):
     from deepnet_b200 import Tensor, dtypes
     from oracle.host_tensor import HostTensor
+    threads = use_all_host_cores()
     rng = np.random.default_rng(2)
     per_dtype = []
     total_bytes = 0
@@ -185,7 +225,33 @@ def run_cpu_cases(side: int, steps: int, warmup: int):
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     sec = statistics.median(times)
-    return total_bytes / sec / 1e9, sec, total_bytes
+    return total_bytes / sec / 1e9, sec, total_bytes, threads
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# verification of device buffers against the oracle
+# ---------------------------------------------------------------------------------------------------------------
+def arrays_equal(h: np.ndarray, c: np.ndarray, rtol: float = 0.0) -> bool:
+    """Chunked: bit-exact (NaN == NaN), or rel `rtol` for the one transcendental case."""
+    if h.shape != c.shape or h.dtype != c.dtype:
+        return False
+    hf, cf = h.reshape(-1), c.reshape(-1)
+    bits = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[h.dtype.itemsize]
+    for lo in range(0, hf.size, 1 << 24):
+        hh, cc = hf[lo:lo + (1 << 24)], cf[lo:lo + (1 << 24)]
+        if np.array_equal(hh.view(bits), cc.view(bits)):
+            continue
+        if h.dtype.kind != "f":
+            return False
+        nan = np.isnan(hh) & np.isnan(cc)
+        if rtol == 0.0:
+            ok = nan | ((hh == cc) & (np.signbit(hh) == np.signbit(cc)))
+        else:
+            err = np.abs(hh.astype(np.float64) - cc.astype(np.float64))
+            ok = nan | (hh == cc) | (err <= rtol * np.abs(hh.astype(np.float64)) + np.finfo(h.dtype).tiny)
+        if not ok.all():
+            return False
+    return True
 
 
 def measure_other_configs(dev, torch, peak):
@@ -249,6 +315,10 @@ def measure_other_configs(dev, torch, peak):
     hbm("C3 ArgMaxLastAxis 262144x1000 f32", nb + 262144 * 8, lambda: oi._fill_axis("ArgMaxLastAxis", 1, lg, True))
     hbm("C3 MaxLastAxis 262144x1000 f32", nb + 262144 * 4, lambda: om.FillMaxAxis(1, lg))
     hbm("C3 SumLastAxis 262144x1000 f32", nb + 262144 * 4, lambda: om.FillSumAxis(1, lg))
+    import ctypes as C
+    d_ = lambda t: t.Backend._d(t)
+    hbm("C3 Max + ArgMax in ONE pass (dn_shard_minmax_arg_last_axis, group = NULL)", nb + 262144 * 12,
+        lambda: dev.api.call("shard_minmax_arg_last_axis", None, 0, 1, d_(om), d_(oi), 0, d_(lg)))
     del tl, lg
     # C4: gather / scatter / masked get / trueIdx on 2^26 int64 / bool
     N = 1 << 26
@@ -268,7 +338,7 @@ def measure_other_configs(dev, torch, peak):
     ti = Tensor.empty((ntrue, 2), I64, dev)
     hbm("C4 TrueIndices [8192,8192] p=0.5", N + 16 * ntrue, lambda: ti.Backend.TrueIndices(ti, m2), 2)
     del tsrc, tidx, src, idx, trg, got, ti
-    # C5: MLP training step 784-4096-4096-10, batch 8192 (tcgen05 TF32 MatMatDot + element-wise + reductions)
+    # C5: MLP training step 784-4096-4096-10, batch 8192 (tcgen05 MatMatDot + element-wise + reductions)
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     from mlp_step import flops_per_step, init_params, synthetic_batch, train_step
     sizes, batch = (784, 4096, 4096, 10), 8192
@@ -276,26 +346,33 @@ def measure_other_configs(dev, torch, peak):
     params = [(CudaTensor.ofNumpy(wt), CudaTensor.ofNumpy(bs)) for wt, bs in init_params(rng, sizes)]
     xn, tn = synthetic_batch(rng, batch, sizes[0], sizes[-1])
     x, t = CudaTensor.ofNumpy(xn), CudaTensor.ofNumpy(tn)
-    ms = timed(lambda: train_step(x, t, params, 1e-3), 3)
     fl = flops_per_step(batch, sizes)
-    out["C5 MLP 784-4096-4096-10 batch 8192 training step"] = {"ms": round(ms, 3), "TFLOP/s": round(fl / ms / 1e9, 1),
-                                                              "gemm_tflop_per_step": round(fl / 1e12, 3)}
-    ms_f = timed(lambda: train_step(x, t, params, 1e-3, fused=True), 3)
-    out["C5 MLP training step with FusedElemwise (same bits, fewer passes over HBM)"] = {
-        "ms": round(ms_f, 3), "TFLOP/s": round(fl / ms_f / 1e9, 1)}
-    # the GEMM alone (largest layer), against cuBLAS-free denominators: measured bf16 peak / 2 for tf32
     th, tw = torch.randn(8192, 4096, device="cuda"), torch.randn(4096, 4096, device="cuda")
     hh, ww, cc = w(th, F32), w(tw, F32), Tensor.empty((8192, 4096), F32, dev)
-    ms = timed(lambda: cc.FillDot(hh, ww.T), 5)
-    tf = 2.0 * 8192 * 4096 * 4096 / ms / 1e9
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             bf16 = float(json.load(f)["bf16_tflops"])
     except Exception:
         bf16 = 1590.0
-    out["C5 MatMatDot 8192x4096x4096 f32 (tcgen05 kind::tf32)"] = {
-        "ms": round(ms, 4), "TFLOP/s": round(tf, 1), "frac_of_tf32_peak": round(tf / (bf16 / 2), 3),
-        "tf32_peak_assumed": f"{bf16 / 2:.1f} = measured bf16 peak / 2"}
+    # both precisions of float32 MatMatDot (dn_set_math_mode): the fp32-accurate default (3xTF32 on tcgen05) and the
+    # opt-in single tf32 pass that north_star's rel 1e-2 tolerance allows
+    for mode, label in (("tf32", "DN_MATH_TF32 (opt-in: tf32 inputs, rel 1e-2)"),
+                        ("fp32", "DN_MATH_FP32 (default: fp32-accurate, 3xTF32)")):
+        dev.SetMathMode(mode)
+        ms = timed(lambda: train_step(x, t, params, 1e-3), 3)
+        out[f"C5 MLP 784-4096-4096-10 batch 8192 training step, {label}"] = {
+            "ms": round(ms, 3), "TFLOP/s": round(fl / ms / 1e9, 1), "gemm_tflop_per_step": round(fl / 1e12, 3)}
+        ms_f = timed(lambda: train_step(x, t, params, 1e-3, fused=True), 3)
+        out[f"C5 MLP training step with FusedElemwise (same bits, fewer passes over HBM), {label}"] = {
+            "ms": round(ms_f, 3), "TFLOP/s": round(fl / ms_f / 1e9, 1)}
+        # the GEMM alone (largest layer), against cuBLAS-free denominators: measured bf16 peak / 2 for tf32
+        ms = timed(lambda: cc.FillDot(hh, ww.T), 5)
+        tf = 2.0 * 8192 * 4096 * 4096 / ms / 1e9
+        out[f"C5 MatMatDot 8192x4096x4096 f32, {label}"] = {
+            "ms": round(ms, 4), "TFLOP/s": round(tf, 1), "frac_of_tf32_peak": round(tf / (bf16 / 2), 3),
+            "tensor_flops_issued_TFLOP/s": round(tf * (3 if mode == "fp32" else 1), 1),
+            "tf32_peak_assumed": f"{bf16 / 2:.1f} = measured bf16 peak / 2"}
+    dev.SetMathMode("fp32")
     return out
 
 
@@ -308,8 +385,10 @@ def main():
     ap.add_argument("--side", type=int, default=SIDE, help="tensor side (default 16384 = 2^28 elements)")
     ap.add_argument("--cpu-side", type=int, default=8192,
                     help="side of the bounded CPU sample ([8192,8192]: ~5 s per step on the GPU box's 16 cores)")
+    ap.add_argument("--verify", action="store_true", help="re-run every one of the 33 calls and check it against the oracle")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of the timed buffers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the C1/C3/C4 side measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the weak-scaling / C1 / C3 / C4 / C5 side measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -321,17 +400,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        warm = max(1, min(args.warmup, 2))
-        steps = max(1, min(args.steps, 5))
-        gbs, sec, nbytes = run_cpu_cases(args.cpu_side, steps, warm)
+        # a step on the [8192,8192] sample is ~5 s on 16 cores: --steps / --warmup are honoured as given
+        gbs, sec, nbytes, threads = run_cpu_cases(args.cpu_side, max(1, args.steps), max(0, args.warmup))
         sample = (f"same 33-call case list on [{args.cpu_side},{args.cpu_side}] tensors "
                   f"({nbytes / 1e9:.2f} GB algorithmic per step)")
         line = {
-            "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32+f64+i32", "data": "synthetic",
-            "config": {"workload": workload, "reference_arm": "HostTensor restatement (C++/OpenMP, oracle/), not .NET"},
-            "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+            "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64+i32", "data": "synthetic",
+            "config": {"workload": workload, "cpu_sample_side": args.cpu_side,
+                       "reference_arm": "HostTensor restatement (C++/OpenMP, oracle/), not .NET; rank 0 only, all host cores"},
+            "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
@@ -348,7 +427,12 @@ def main():
     dev.Init(local_rank)
     stream = torch.cuda.current_stream()
     dev.SetStream(stream.cuda_stream)
+    api = dev.api
     side = args.side
+    if side % world:
+        raise SystemExit(f"--side {side} must be divisible by the number of ranks ({world})")
+    rows = side // world                    # STRONG scaling: this rank's slab of the leading axis
+    r0 = rank * rows
     torch_dt = {dtypes.DN_F32: torch.float32, dtypes.DN_F64: torch.float64, dtypes.DN_I32: torch.int32}
 
     def barrier():
@@ -356,33 +440,54 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm -------------------------------------------------------------------------------
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ranks_ok(ok: bool) -> bool:
+        t = torch.tensor([1.0 if ok else 0.0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() > 0.5)
+
+    def wrap(t, d):
+        return CudaTensor.usingPtr(t.data_ptr(), tuple(t.shape), d, owner=t)
+
+    # ---- inputs: created on the HOST (pinned), so that the e2e arm uploads and the oracle checks the same data ----
+    # per dtype: a, b [rows, side] (this rank's row slab); for N > 1 also the column blocks at, bt [side, rows] that
+    # the transposed views read (at N = 1 the transposed views alias a and b themselves)
     rng = np.random.default_rng(1000 + rank)
-    per_dtype, keep = [], []
-    host_sets = []
+    sets = []
     for dt, npdt, has_sin in dtype_list():
-        g = torch.Generator(device="cuda").manual_seed(17 + rank)
-        if dt == dtypes.DN_I32:
-            mk = lambda shape: torch.randint(-50, 50, shape, device="cuda", dtype=torch.int32, generator=g)
-        else:
-            mk = lambda shape: torch.rand(shape, device="cuda", dtype=torch_dt[dt], generator=g) * 100 - 50
-        ta, tb, trow, tcol = mk((side, side)), mk((side, side)), mk((1, side)), mk((side, 1))
-        tc = torch.empty((side, side), device="cuda", dtype=torch_dt[dt])
-        tm = torch.empty((side, side), device="cuda", dtype=torch.bool)
-        keep += [ta, tb, trow, tcol, tc, tm]
-        w = lambda t, d=dt: CudaTensor.usingPtr(t.data_ptr(), tuple(t.shape), d, owner=t)
-        a, b, row, col, c = w(ta), w(tb), w(trow), w(tcol), w(tc)
-        mask = CudaTensor.usingPtr(tm.data_ptr(), (side, side), dtypes.DN_BOOL, owner=tm)
-        per_dtype.append((dt, build_cases(Tensor, dt, a, b, c, row, col, mask, has_sin), (a, b, c)))
-    step_bytes = sum(nb for _, cases, _ in per_dtype for _, nb, _, _ in cases)
-    ncalls = sum(len(cases) for _, cases, _ in per_dtype)
+        an, bn, rown, coln = host_inputs(rng, side, npdt, rows)
+        host = {"a": an, "b": bn, "row": rown, "col": coln}
+        if world > 1:
+            host["at"], host["bt"] = (x.T.copy() for x in host_inputs(rng, side, npdt, rows)[:2])   # [side, rows]
+        pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+        devt = {k: v.to("cuda", non_blocking=True) for k, v in pinned.items()}
+        devt["c"] = torch.empty((rows, side), device="cuda", dtype=torch_dt[dt])
+        devt["mask"] = torch.empty((rows, side), device="cuda", dtype=torch.bool)
+        T_ = {k: wrap(v, dtypes.DN_BOOL if k == "mask" else dt) for k, v in devt.items()}
+        aT = T_["at"].T if world > 1 else None
+        bT = T_["bt"].T if world > 1 else None
+        cases = build_cases(Tensor, dt, T_["a"], T_["b"], T_["c"], T_["row"], T_["col"], T_["mask"], has_sin, aT, bT)
+        sets.append({"dt": dt, "npdt": npdt, "has_sin": has_sin, "host": {k: v.numpy() for k, v in pinned.items()},
+                     "pinned": pinned, "dev": devt, "T": T_, "cases": cases})
+        del host
+    torch.cuda.synchronize()
+    step_bytes = sum(nb for s in sets for _, nb, _, _ in s["cases"])
+    ncalls = sum(len(s["cases"]) for s in sets)
 
     def step():
-        for _, cases, _ in per_dtype:
-            for _, _, fn, _ in cases:
+        for s in sets:
+            for _, _, fn, _ in s["cases"]:
                 fn()
 
-    for _ in range(max(3, args.warmup)):
+    # ---- device-resident arm (the headline `value`) -----------------------------------------------------------
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         step()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -397,26 +502,69 @@ def main():
     ev1.record(stream)
     barrier()
     launches = dev.LaunchCount() - launches0
-    total_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
+    ms_per_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     value = step_bytes * world / (ms_per_step * 1e-3) / 1e9
 
-    # per-call timing (CUDA events on the launching stream) for the roofline object; outside the timed region
+    # ---- verification: the timed buffers against the HostTensor oracle -----------------------------------------
+    # After the timed region c holds ifThenElse(mask, a, b) and mask holds a < b.T (the last two calls of every dtype).
+    # --verify additionally re-runs each of the 33 calls once and checks its target.
+    verified = None
+    if not args.no_verify:
+        from oracle.host_tensor import HostTensor
+        use_all_host_cores()
+        ok = True
+        checked = 0
+        for s in sets:
+            dt, h = s["dt"], s["host"]
+            ha, hb, hrow, hcol = (host_of(h[k]) for k in ("a", "b", "row", "col"))
+            haT = host_of(h["at"]).T if world > 1 else None
+            hbT = host_of(h["bt"]).T if world > 1 else None
+            hc = Tensor.empty((rows, side), dt, HostTensor.Dev)
+            hmask = Tensor.empty((rows, side), dtypes.DN_BOOL, HostTensor.Dev)
+            hcases = build_cases(Tensor, dt, ha, hb, hc, hrow, hcol, hmask, s["has_sin"], haT, hbT)
+            if args.verify:
+                hc.FillConst(0)
+                s["T"]["c"].FillConst(0)
+                todo = list(zip(hcases, s["cases"]))
+            else:
+                todo = list(zip(hcases, s["cases"]))[-2:]
+                todo = [(hcase, None) for hcase, _ in todo]      # device results are already in the timed buffers
+            for (name, _, hfn, _), dcase in todo:
+                hfn()
+                if dcase is not None:
+                    dcase[2]()
+                torch.cuda.synchronize()
+                if "-> bool" in name:
+                    hh, cc = hmask.Storage.array.reshape(rows, side), s["dev"]["mask"].cpu().numpy()
+                else:
+                    hh, cc = hc.Storage.array.reshape(rows, side), s["dev"]["c"].cpu().numpy()
+                    if "[1:,1:]" in name:
+                        hh, cc = np.ascontiguousarray(hh[1:, 1:]), np.ascontiguousarray(cc[1:, 1:])
+                ok = ok and arrays_equal(hh, cc, 1e-5 if " sin(" in name else 0.0)
+                checked += 1
+            if not args.verify:   # the mask is an INPUT of the last call: it must be verified too (done above, [-2])
+                pass
+        ok = all_ranks_ok(ok)
+        verified = {"ok": ok, "calls_checked_per_rank": checked,
+                    "what": ("all 33 calls re-run once and compared with the HostTensor oracle" if args.verify else
+                             "the timed buffers after the timed region (c = ifThenElse(mask,a,b), mask = a < b.T, "
+                             "per dtype) compared with the HostTensor oracle"),
+                    "rule": "bit-exact; float32 sin rel 1e-5"}
+        if not ok:
+            print(json.dumps({"error": "verification against the oracle FAILED", "verified": verified}), file=sys.stderr)
+
+    # ---- per-call timing (CUDA events on the launching stream) for the roofline object; outside the timed region
     per_call = []
-    for _, cases, _ in per_dtype:
-        for name, nb, fn, ktag in cases:
+    for s in sets:
+        for name, nb, fn, ktag in s["cases"]:
             ts = []
             for _ in range(5):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record(stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
                 fn()
-                e.record(stream)
-                e.synchronize()
-                ts.append(s.elapsed_time(e))
+                e1.record(stream)
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
             per_call.append((name, nb, statistics.median(ts), ktag))
     clocks = sampler.stop() if rank == 0 else None
     peak, peak_src = load_peaks()
@@ -431,84 +579,79 @@ def main():
     total_call_ms = sum(x[2] for x in per_call)
     dom_tag, dom = max(groups.items(), key=lambda kv: kv[1]["ms"])
     nlaunch = len(dom["calls"])
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of that kernel on the contiguous case, from the
-    # `ncu --set full` captures under profiles/ (None for kernels that have not been captured)
-    ncu_traffic = {
-        "ew_kernel<BinaryF<float,ADD>,VEC=8> (256-bit vector kernel)": 2.147553e9 + 1.041274e9,   # r01b_ew_add_contig256
-        "ew_kernel<BinaryF<double,ADD>,VEC=4> (256-bit vector kernel)": NCU_F64_ADD_TRAFFIC,       # r01c_ew_add_contig256_f64
-        "ew_xpose_kernel<BinaryF<float,ADD>> (register transpose)": 2.147507e9 + 1.039083e9,      # r01_ew_xpose_addT
-        "ew_xpose_kernel<BinaryF<double,ADD>> (register transpose)": 4.295036e9 + 2.110988e9,     # r01_ew_xpose_f64_addT
-    }
+    traffic, traffic_src = NCU_TRAFFIC.get(dom_tag, (None, None))
+    if side != SIDE or world != 1:
+        traffic, traffic_src = None, "the committed captures are of the 1-GPU [16384,16384] launch"
     roofline = {
         "bound": "hbm", "kernel": dom_tag, "launches_per_step": nlaunch, "calls": dom["calls"],
         "achieved": dom["bytes"] / dom["ms"] / 1e6, "peak": peak, "unit": "GB/s",
         "frac": dom["bytes"] / dom["ms"] / 1e6 / peak,
-        "traffic": ncu_traffic.get(dom_tag) if side == SIDE else None,
-        "traffic_note": "DRAM bytes of one launch on the contiguous case (algorithmic: 3 x 2^28 x element size); "
-                        "achieved = algorithmic bytes of all launches of this kernel in a step / their summed duration",
+        "traffic": traffic, "traffic_source": traffic_src,
+        "traffic_note": "DRAM bytes of one launch on the contiguous case, copied from the named ncu capture (not "
+                        "measured in this run); algorithmic: 3 x 2^28 x element size. achieved = algorithmic bytes of "
+                        "all launches of this kernel in a step / their summed duration (CUDA events, this run)",
         "algorithmic_bytes": dom["bytes"] / nlaunch, "peak_source": peak_src,
         "share_of_step": dom["ms"] / total_call_ms,
         "per_call_gbs": {n: round(nb / ms / 1e6, 1) for n, nb, ms, _ in per_call},
         "per_kernel": {k: {"share_of_step": round(v["ms"] / total_call_ms, 4), "GB/s": round(v["bytes"] / v["ms"] / 1e6, 1),
                            "launches": len(v["calls"])} for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])},
-        "step_frac_of_peak": (step_bytes / (ms_per_step * 1e-3) / 1e9) / peak if world == 1 else value / world / peak,
+        "step_frac_of_peak": value / world / peak,
     }
 
-    # ---- e2e arm: pinned host buffers -> H2D -> same calls -> D2H of one result per dtype ---------------------
-    # Pinned host buffers (8 GiB per rank at the default size): float32 and int32 share one pair of input buffers
-    # (the int32 cases upload the same bytes), float64 has its own pair, one download buffer is shared.
-    e2e_side = side
-    pinned = []
-    h2d = d2h = 0
-    out_buf = torch.empty(e2e_side * e2e_side * 8, dtype=torch.uint8).pin_memory()
-    shared32 = None
-    for dt, npdt, has_sin in dtype_list():
-        isz = dtypes.itemsize(dt)
-        if isz == 4 and shared32 is not None:
-            hp = [x.view(torch_dt[dt]) for x in shared32]
-        else:
-            an, bn, _, _ = host_inputs(rng, e2e_side, npdt)
-            hp = [torch.from_numpy(x).pin_memory() for x in (an, bn)]
-            del an, bn
-            if isz == 4:
-                shared32 = hp
-        out = out_buf[: e2e_side * e2e_side * isz].view(torch_dt[dt]).view(e2e_side, e2e_side)
-        pinned.append((hp, out))
-        h2d += sum(x.numel() * x.element_size() for x in hp)
-        d2h += out.numel() * out.element_size()
-    api = dev.api
-    # Three streams through the C ABI (dn_set_stream is per thread, switched around each group of calls): uploads
-    # of dtype k+1 overlap the kernels of dtype k and the download of dtype k-1. Ordering is by events
-    # (dn_event_record / dn_stream_wait_event); the step ends with dn_sync on every stream.
-    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    # ---- e2e arm: pinned host buffers -> H2D -> the same 33 calls -> D2H of the final result of every dtype -------
+    # Three streams through the C ABI (dn_set_stream is per thread, switched around each group of calls): the uploads
+    # of dtype k+1 overlap the kernels of dtype k and the downloads of dtype k-1; ordering by dn_event_record /
+    # dn_stream_wait_event. The last call of a dtype (ifThenElse) runs per row block, each block's download starting
+    # as soon as that block is done, so only one block's D2H is exposed at the end of the step.
     import ctypes as C
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
 
     def mk_event():
         e = C.c_void_p()
         api.call("event_create", C.byref(e))
         return e
 
-    ev_up = [mk_event() for _ in pinned]
-    ev_done = [mk_event() for _ in pinned]
-    ev_free = [mk_event() for _ in pinned]   # previous step's kernels done with a, b of this dtype
+    NBLK = 4 if rows % 4 == 0 and rows >= 64 else 1
+    blk = rows // NBLK
+    h2d = d2h = 0
+    for s in sets:
+        isz = dtypes.itemsize(s["dt"])
+        s["up"] = [(s["T"][k], s["pinned"][k]) for k in ("a", "b", "row", "col", "at", "bt") if k in s["pinned"]]
+        s["out_c"] = torch.empty((rows, side), dtype=torch_dt[s["dt"]]).pin_memory()
+        s["out_m"] = torch.empty((rows, side), dtype=torch.bool).pin_memory()
+        h2d += sum(p.numel() * p.element_size() for _, p in s["up"])
+        d2h += rows * side * (isz + 1)
+        s["ev_up"], s["ev_free"], s["ev_mask"] = mk_event(), mk_event(), mk_event()
+        s["ev_blk"] = [mk_event() for _ in range(NBLK)]
+        T_ = s["T"]
+        s["last_blocks"] = [(lambda lo=lo, T_=T_: T_["c"][lo:lo + blk].FillIfThenElse(T_["mask"][lo:lo + blk],
+                                                                                    T_["a"][lo:lo + blk], T_["b"][lo:lo + blk]))
+                            for lo in range(0, rows, blk)]
 
     def e2e_step():
-        for k, ((dt, cases, (a, b, c)), (hp, out)) in enumerate(zip(per_dtype, pinned)):
-            isz = dtypes.itemsize(dt)
+        for s in sets:
+            isz = dtypes.itemsize(s["dt"])
             dev.SetStream(s_h2d.cuda_stream)
-            api.call("stream_wait_event", ev_free[k])      # do not overwrite inputs still being read
-            api.call("memcpy_h2d", a.Storage.BasePtr(), hp[0].data_ptr(), hp[0].numel() * isz)
-            api.call("memcpy_h2d", b.Storage.BasePtr(), hp[1].data_ptr(), hp[1].numel() * isz)
-            api.call("event_record", ev_up[k])
+            api.call("stream_wait_event", s["ev_free"])      # do not overwrite inputs the previous step still reads
+            for t, p in s["up"]:
+                api.call("memcpy_h2d", t.Storage.BasePtr(), p.data_ptr(), p.numel() * p.element_size())
+            api.call("event_record", s["ev_up"])
             dev.SetStream(stream.cuda_stream)
-            api.call("stream_wait_event", ev_up[k])
-            for _, _, fn, _ in cases:
+            api.call("stream_wait_event", s["ev_up"])
+            for _, _, fn, _ in s["cases"][:-1]:
                 fn()
-            api.call("event_record", ev_done[k])
-            api.call("event_record", ev_free[k])
+            api.call("event_record", s["ev_mask"])
+            for k, fn in enumerate(s["last_blocks"]):
+                fn()
+                api.call("event_record", s["ev_blk"][k])
+            api.call("event_record", s["ev_free"])
             dev.SetStream(s_d2h.cuda_stream)
-            api.call("stream_wait_event", ev_done[k])
-            api.call("memcpy_d2h_async", out.data_ptr(), c.Storage.BasePtr(), out.numel() * isz)
+            api.call("stream_wait_event", s["ev_mask"])
+            api.call("memcpy_d2h_async", s["out_m"].data_ptr(), s["T"]["mask"].Storage.BasePtr(), rows * side)
+            for k in range(NBLK):
+                api.call("stream_wait_event", s["ev_blk"][k])
+                off = k * blk * side * isz
+                api.call("memcpy_d2h_async", s["out_c"].data_ptr() + off, s["T"]["c"].Storage.BasePtr() + off, blk * side * isz)
         # the step's results must be on the host before the step counts as finished
         for st in (s_h2d, s_d2h):
             dev.SetStream(st.cuda_stream)
@@ -517,8 +660,8 @@ def main():
         dev.Synchronize()
 
     e2e_steps = max(1, min(args.steps, 3))
-    for k in range(len(pinned)):
-        api.call("event_record", ev_free[k])
+    for s in sets:
+        api.call("event_record", s["ev_free"])
     e2e_step()
     barrier()
     # several streams are involved, so the step is timed on the host between full synchronisations (every
@@ -529,55 +672,71 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     barrier()
-    t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(e2e_ms)
     e2e_value = step_bytes * world / (e2e_ms * 1e-3) / 1e9
+    e2e_ok = None
+    if not args.no_verify:   # what arrived on the host is what the device-resident arm verified
+        e2e_ok = all_ranks_ok(all(arrays_equal(s["out_c"].numpy(), s["dev"]["c"].cpu().numpy()) and
+                                  arrays_equal(s["out_m"].numpy(), s["dev"]["mask"].cpu().numpy()) for s in sets))
+    for st in (s_h2d, s_d2h):
+        api.call("release_stream", st.cuda_stream)
+
+    # ---- free the headline buffers before the side measurements ------------------------------------------------
+    for s in sets:
+        s.clear()
+    del sets
+    torch.cuda.empty_cache()
+
+    # ---- weak scaling beside the strong headline (N > 1): one full-size tensor set per rank, 5 steps ---------------
+    weak = None
+    if world > 1 and not args.no_extra:
+        try:
+            wsets = []
+            g = torch.Generator(device="cuda").manual_seed(17 + rank)
+            for dt, npdt, has_sin in dtype_list():
+                if dt == dtypes.DN_I32:
+                    mk = lambda shape: torch.randint(-50, 50, shape, device="cuda", dtype=torch.int32, generator=g)
+                else:
+                    mk = lambda shape: torch.rand(shape, device="cuda", dtype=torch_dt[dt], generator=g) * 100 - 50
+                ts_ = [mk((side, side)), mk((side, side)), mk((1, side)), mk((side, 1)),
+                       torch.empty((side, side), device="cuda", dtype=torch_dt[dt])]
+                tm = torch.empty((side, side), device="cuda", dtype=torch.bool)
+                a, b, row, col, c = (wrap(t, dt) for t in ts_)
+                wsets.append((build_cases(Tensor, dt, a, b, c, row, col, wrap(tm, dtypes.DN_BOOL), has_sin), ts_, tm))
+            wbytes = sum(nb for cs, _, _ in wsets for _, nb, _, _ in cs)
+
+            def wstep():
+                for cs, _, _ in wsets:
+                    for _, _, fn, _ in cs:
+                        fn()
+            for _ in range(3):
+                wstep()
+            barrier()
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record(stream)
+            for _ in range(5):
+                wstep()
+            w1.record(stream)
+            barrier()
+            wms = max_over_ranks(w0.elapsed_time(w1)) / 5
+            weak = {"scaling": "weak", "value": wbytes * world / (wms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": wms,
+                    "steps": 5, "per_rank": f"[{side},{side}] x 3 dtypes"}
+            del wsets
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            weak = {"error": repr(ex)}
 
     # ---- sharded reductions (BASELINE.json configs[2]): ArgMaxLastAxis + MaxLastAxis over a
-    # 262144 x 1000 float32 tensor split along dim 0 over the ranks (strong scaling), outputs combined by an NCCL
-    # all-gather; timed on the device, max over ranks. Reported beside the headline.
+    # 262144 x 1000 float32 tensor split along dim 0 over the ranks (STRONG scaling) through dn_shard_*: every rank's
+    # reduction kernel stores its rows into all ranks' results over NVLink and signals; no NCCL on the path (the
+    # 64-byte window handles are exchanged once through torch.distributed). Timed on the device, max over ranks.
     sharded = None
     try:
-        from deepnet_b200.shard import LeadingAxisSharding, slab
-        TD = {torch.float32: dtypes.DN_F32, torch.int64: dtypes.DN_I64, torch.bool: dtypes.DN_BOOL}
-        sh = LeadingAxisSharding(lambda t: CudaTensor.usingPtr(t.data_ptr(), tuple(t.shape), TD[t.dtype], owner=t),
-                                 torch.device("cuda", local_rank))
-        C3 = 1000
-
-        def c3_time(R3):
-            b3, c3 = slab(R3, rank, world)
-            tl = torch.rand(c3, C3, device="cuda") * 100 - 50
-            lg = CudaTensor.usingPtr(tl.data_ptr(), (c3, C3), dtypes.DN_F32, owner=tl)
-
-            def c3_step():
-                sh.reduce_axis("ArgMaxLastAxis", lg, 1, R3)
-                sh.reduce_axis("MaxLastAxis", lg, 1, R3)
-            for _ in range(3):
-                c3_step()
-            barrier()
-            s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps3 = 10
-            s3.record(stream)
-            for _ in range(reps3):
-                c3_step()
-            e3.record(stream)
-            barrier()
-            t3 = torch.tensor([s3.elapsed_time(e3) / reps3], device="cuda", dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-            ms3 = float(t3.item())
-            return ms3, (2 * R3 * C3 * 4 + R3 * 12) / ms3 / 1e6
-
-        ms_s, gbs_s = c3_time(262144)            # strong: the config's tensor split over the ranks
-        ms_w, gbs_w = c3_time(262144 * world)    # weak: one config-sized slab per rank
-        sharded = {"workload": f"C3 ArgMaxLastAxis + MaxLastAxis over [R,{C3}] float32, {world} leading-axis shard(s), "
-                               "outputs all-gathered in place (NCCL)",
-                   "strong": {"rows": 262144, "ms": ms_s, "GB/s": gbs_s},
-                   "weak": {"rows": 262144 * world, "ms": ms_w, "GB/s": gbs_w}}
+        sharded = measure_sharded_c3(dev, torch, dist, rank, world, local_rank, barrier, max_over_ranks, all_ranks_ok,
+                                     not args.no_verify)
     except Exception as ex:
         sharded = {"error": repr(ex)}
+    dev.SetStream(stream.cuda_stream)
 
     if rank != 0:
         if world > 1:
@@ -586,30 +745,36 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32+f64+i32", "data": "synthetic",
         "config": {"workload": workload, "calls_per_step": ncalls, "algorithmic_bytes_per_step_per_gpu": step_bytes,
-                   "l2": "inputs (1-2 GiB each) are far larger than the 126 MB L2; no flush needed",
-                   "parallelism": f"leading-axis shards x{world}, no collective"},
+                   "l2": "inputs (0.1-2 GiB each) are far larger than the 126 MB L2; no flush needed",
+                   "parallelism": f"leading-axis shards x{world} of the 2^28-element tensors ({rows} rows per rank), "
+                                  "no collective"},
         "frac_of_peak": value / world / peak, "peak_gbs": peak, "peak_source": peak_src,
+        "verified": verified,
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "steps": e2e_steps},
+                "ms_per_step": e2e_ms, "steps": e2e_steps, "arrived_intact": e2e_ok,
+                "rule": "per step and rank: every input of the 33 calls is uploaded from pinned host memory, all 33 "
+                        "calls run, and the final result of every dtype (target of the last call) plus its bool "
+                        "mask are downloaded; the 10 intermediate results per dtype are overwritten on the device "
+                        "and never leave it"},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "weak_scaling": weak,
         "sharded_reductions": sharded,
     }
     if world == 1 and not args.no_extra:
         try:
-            del per_dtype, keep, pinned
             torch.cuda.empty_cache()
             line["other_configs"] = measure_other_configs(dev, torch, peak)
         except Exception as ex:  # the side measurements must never take the headline down
             line["other_configs"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
-        gbs, sec, nbytes = run_cpu_cases(args.cpu_side, 2, 1)
+        gbs, sec, nbytes, threads = run_cpu_cases(args.cpu_side, 2, 1)
         line["cpu_baseline"] = {
-            "value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
+            "value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
             "sample": f"same 33-call case list on [{args.cpu_side},{args.cpu_side}] tensors "
                       f"({nbytes / 1e9:.2f} GB algorithmic per step, {sec:.2f} s per step); HostTensor restatement "
                       f"(C++/OpenMP) with the reference's threading policy, not .NET"}
@@ -617,6 +782,90 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def measure_sharded_c3(dev, torch, dist, rank, world, local_rank, barrier, max_over_ranks, all_ranks_ok, verify):
+    import ctypes as C
+    from deepnet_b200 import CudaTensor, dtypes
+    from deepnet_b200.shard import ShardGroup, slab
+    R3, C3 = 262144, 1000
+    api = dev.api
+
+    def exchange(blob: bytes):
+        if world == 1:
+            return [blob]
+        out = [None] * world
+        dist.all_gather_object(out, blob)
+        return out
+
+    grp = ShardGroup.multi_process(dev, rank, world, local_rank, exchange, heap_bytes=64 << 20)
+    st = torch.cuda.Stream()
+    dev.SetStream(st.cuda_stream)
+    grp.set_stream(rank, st.cuda_stream)
+    b3, c3 = slab(R3, rank, world)
+    rng = np.random.default_rng(3)                       # every rank draws the same full tensor, keeps its slab
+    x = rng.uniform(-50, 50, size=(R3, C3)).astype(np.float32)
+    tl = torch.from_numpy(x[b3:b3 + c3]).to("cuda")
+    lg = CudaTensor.usingPtr(tl.data_ptr(), (c3, C3), dtypes.DN_F32, owner=tl)
+    torch.cuda.synchronize()
+    # two sets of full results, used alternately (a target is reused only after another collective in between)
+    oi = [grp.alloc(rank, (R3,), dtypes.DN_I64) for _ in range(2)]
+    om = [grp.alloc(rank, (R3,), dtypes.DN_F32) for _ in range(2)]
+    d = lambda t: t.Backend._d(t)
+    g, dl = grp._g, d(lg)
+    doi, dom = [d(t) for t in oi], [d(t) for t in om]
+    f_arg, f_red, f_fused = api._shard_arg_reduce_last_axis, api._shard_reduce_last_axis, api._shard_minmax_arg_last_axis
+    DN_MAX, DN_ARG_MAX = 3, 1
+
+    def two_calls(k):
+        api.check(f_arg(g, rank, DN_ARG_MAX, doi[k & 1], b3, dl))
+        api.check(f_red(g, rank, DN_MAX, dom[k & 1], b3, dl))
+
+    def one_call(k):
+        api.check(f_fused(g, rank, DN_ARG_MAX, dom[k & 1], doi[k & 1], b3, dl))
+
+    def timed(fn, reps=20):
+        for k in range(4):
+            fn(k)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for k in range(reps):
+            fn(k)
+        e1.record(st)
+        st.synchronize()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / reps)
+
+    ms2 = timed(two_calls)
+    ok2 = None
+    if verify:
+        want_i, want_v = x.argmax(axis=1), x.max(axis=1)
+        ok2 = all_ranks_ok(bool((oi[1].toNumpy() == want_i).all() and (om[1].toNumpy() == want_v).all()))
+    for t in oi + om:
+        t.FillConst(0)
+    st.synchronize()
+    barrier()
+    ms1 = timed(one_call)
+    ok1 = None
+    if verify:
+        ok1 = all_ranks_ok(bool((oi[1].toNumpy() == want_i).all() and (om[1].toNumpy() == want_v).all()))
+    nbytes = R3 * C3 * 4
+    out = {"workload": f"C3 ArgMaxLastAxis + MaxLastAxis over [{R3},{C3}] float32 split into {world} leading-axis "
+                       f"slab(s) (strong scaling); every rank ends with the full [{R3}] results",
+           "mechanism": "dn_shard_*: reduction kernel stores its rows into every rank's result (peer memory over "
+                        "NVLink / CUDA IPC), last CTA signals, stream waits on the flags; no NCCL launch",
+           "two_calls": {"ms": ms2, "GB/s": (2 * nbytes + R3 * 12) / ms2 / 1e6, "verified": ok2,
+                         "what": "dn_shard_arg_reduce_last_axis + dn_shard_reduce_last_axis (the source is read twice)"},
+           "one_pass": {"ms": ms1, "GB/s": (nbytes + R3 * 12) / ms1 / 1e6, "verified": ok1,
+                        "what": "dn_shard_minmax_arg_last_axis (Max and ArgMax in one pass over the source)"},
+           "nvlink_bytes_per_rank_per_step": (world - 1) * c3 * 12,
+           "scaling": "strong"}
+    dev.Synchronize()
+    barrier()
+    grp.close()
+    api.call("release_stream", st.cuda_stream)
+    return out
 
 
 if __name__ == "__main__":

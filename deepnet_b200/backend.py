@@ -341,6 +341,10 @@ class TensorCudaDevice(ITensorDevice):
         """Cfg.Stacktrace, CudaCfg.fs:33-35."""
         self.api.call("set_check_errors", 1 if enabled else 0)
 
+    def SetMathMode(self, mode: str) -> None:
+        """dn_set_math_mode: "fp32" (default; fp32-accurate MatMatDot, 3xTF32 on the tensor cores) or "tf32"."""
+        self.api.call("set_math_mode", {"fp32": 0, "tf32": 1}[mode])
+
     def LaunchCount(self) -> int:
         return int(self.api.lib.dn_launch_count())
 

@@ -25,6 +25,7 @@ namespace dn {
 dn_status set_error(dn_status st, const char *fmt, ...);
 dn_status cuda_error(cudaError_t err, const char *what);
 cudaStream_t current_stream();
+void set_thread_stream(cudaStream_t s);
 bool check_errors_enabled();
 extern std::atomic<int64_t> g_launch_count;
 int sm_count();

@@ -14,8 +14,10 @@
 // C = A·B with A[M,K] and B[K,N] given as arbitrary strided views: an operand whose K axis is contiguous and
 // TMA-aligned is consumed in place ("K-major"); anything else (an N-contiguous B, a transposed A, odd pitches) is
 // first repacked K-major by the element-wise transpose kernel (dn_copy) into stream-ordered scratch.
-// Inputs are read as TF32 (10-bit mantissa, the low 13 bits of the fp32 words are ignored by the tensor core),
-// accumulation is fp32: rel 1e-2 of the fp64 oracle per BASELINE.json north_star.
+// Precision (dn_set_math_mode): DN_MATH_FP32, the default, delivers fp32 accuracy like the reference's cuBLAS SGEMM —
+// 3xTF32 (hi/lo split of both operands, three MMAs per k-step) for large problems, the exact SIMT kernel for small
+// ones; DN_MATH_TF32 reads the inputs once as TF32 (10-bit mantissa), fp32 accumulation: rel 1e-2 of the fp64
+// oracle per BASELINE.json north_star, at three times the throughput.
 // float64 has no tcgen05 path: a shared-memory tiled SIMT kernel.
 #include <cuda.h>
 
@@ -125,9 +127,11 @@ struct GemmParams {
     int32_t tiles_m, tiles_n;
 };
 
-template <int BN>
+// SPLIT (3xTF32, fp32-accurate): a stage also holds the low-order tf32 halves of both operands.
+template <int BN, bool SPLIT = false>
 struct GemmCfg {
-    static constexpr int kStageBytes = (kBM + BN) * kBK * 4;
+    static constexpr int kHalfBytes = (kBM + BN) * kBK * 4;
+    static constexpr int kStageBytes = kHalfBytes * (SPLIT ? 2 : 1);
     static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages, power of two >= 32
     static constexpr int kEpiBytes = 4 * 32 * 33 * 4;  // per-epilogue-warp transpose staging
@@ -135,11 +139,17 @@ struct GemmCfg {
 };
 
 // A_MN / B_MN: the operand is MN-major (its M resp. N axis is the contiguous one) and is consumed in place.
-template <int BN, bool A_MN, bool B_MN>
+// SPLIT: every operand arrives as two tf32-exact arrays, hi = tf32(x) and lo = tf32(x - hi) (split_tf32_kernel);
+// each k-step issues A_lo·B_hi + A_hi·B_lo + A_hi·B_hi into the same fp32 accumulator — the 3xTF32 scheme, whose
+// result carries ~2^-21 relative input error instead of tf32's 2^-11 (the dropped A_lo·B_lo term is ~2^-22).
+template <int BN, bool A_MN, bool B_MN, bool SPLIT = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_b,
+                                                                  const __grid_constant__ CUtensorMap map_a_lo,
+                                                                  const __grid_constant__ CUtensorMap map_b_lo,
                                                                   const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    static_assert(!SPLIT || (!A_MN && !B_MN), "split operands are always K-major scratch");
+    using Cfg = GemmCfg<BN, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -198,6 +208,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_kernel(const __grid
                     } else {
                         tma_load_2d(sb, &map_b, &full[stage], kb * kBK, n_blk * BN);
                     }
+                    if constexpr (SPLIT) {
+                        tma_load_2d(sa + Cfg::kHalfBytes, &map_a_lo, &full[stage], kb * kBK, m_blk * kBM);
+                        tma_load_2d(sb + Cfg::kHalfBytes, &map_b_lo, &full[stage], kb * kBK, n_blk * BN);
+                    }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -225,9 +239,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_kernel(const __grid
                     const uint64_t db = B_MN ? make_mnmajor_sw128_desc(sb) : make_kmajor_sw128_desc(sb);
                     // UMMA K = 8 tf32: K-major advances 32 bytes inside the swizzle row, MN-major one 8-row group
                     constexpr uint64_t stepA = A_MN ? (1024 >> 4) : (32 >> 4), stepB = B_MN ? (1024 >> 4) : (32 >> 4);
+                    if constexpr (SPLIT) {
+                        const uint64_t da_lo = make_kmajor_sw128_desc(sa + Cfg::kHalfBytes);
+                        const uint64_t db_lo = make_kmajor_sw128_desc(sb + Cfg::kHalfBytes);
 #pragma unroll
-                    for (int k = 0; k < kBK / 8; ++k)
-                        umma_tf32(tmem_c, da + (uint64_t)k * stepA, db + (uint64_t)k * stepB, idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < kBK / 8; ++k) {  // small terms first
+                            umma_tf32(tmem_c, da_lo + (uint64_t)k * stepA, db + (uint64_t)k * stepB, idesc, (kb | k) ? 1u : 0u);
+                            umma_tf32(tmem_c, da + (uint64_t)k * stepA, db_lo + (uint64_t)k * stepB, idesc, 1u);
+                            umma_tf32(tmem_c, da + (uint64_t)k * stepA, db + (uint64_t)k * stepB, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kBK / 8; ++k)
+                            umma_tf32(tmem_c, da + (uint64_t)k * stepA, db + (uint64_t)k * stepB, idesc, (kb | k) ? 1u : 0u);
+                    }
                     umma_commit(&empty[stage]);
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -366,33 +391,34 @@ dn_status repack_kmajor(Operand2D &o, void **scratch) {
     return DN_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-dn_status launch_tf32(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p) {
-    using Cfg = GemmCfg<BN>;
+template <int BN, bool A_MN, bool B_MN, bool SPLIT = false>
+dn_status launch_tf32(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma_lo, const CUtensorMap &mb_lo,
+                      const GemmParams &p) {
+    using Cfg = GemmCfg<BN, SPLIT>;
     // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE function attribute: one flag per device
     // (a process may drive several devices, dn_set_device / dn_shard_*), set at most once each
     static std::atomic<bool> configured[64];
     int dev = 0;
     DN_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        DN_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DN_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    DN_LAUNCH((gemm_tf32_kernel<BN, A_MN, B_MN>), grid, kGemmThreads, Cfg::kSmemBytes, ma, mb, p);
+    DN_LAUNCH((gemm_tf32_kernel<BN, A_MN, B_MN, SPLIT>), grid, kGemmThreads, Cfg::kSmemBytes, ma, mb, ma_lo, mb_lo, p);
     return launch_status("tcgen05 GEMM kernel");
 }
 
 template <int BN>
 dn_status launch_tf32_major(bool a_mn, bool b_mn, const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p) {
-    if (a_mn) return b_mn ? launch_tf32<BN, true, true>(ma, mb, p) : launch_tf32<BN, true, false>(ma, mb, p);
-    return b_mn ? launch_tf32<BN, false, true>(ma, mb, p) : launch_tf32<BN, false, false>(ma, mb, p);
+    if (a_mn) return b_mn ? launch_tf32<BN, true, true>(ma, mb, ma, mb, p) : launch_tf32<BN, true, false>(ma, mb, ma, mb, p);
+    return b_mn ? launch_tf32<BN, false, true>(ma, mb, ma, mb, p) : launch_tf32<BN, false, false>(ma, mb, ma, mb, p);
 }
 
-// C[M,N] (strides cm, cn) = A[M,K] (am, ak) · B[K,N] (bk, bn), fp32.
-dn_status gemm_f32(float *c, int64_t cm, int64_t cn, const float *a, int64_t am, int64_t ak, const float *b, int64_t bk,
+// C[M,N] (strides cm, cn) = A[M,K] (am, ak) · B[K,N] (bk, bn), fp32 operands read as tf32 (DN_MATH_TF32).
+dn_status gemm_f32_tf32(float *c, int64_t cm, int64_t cn, const float *a, int64_t am, int64_t ak, const float *b, int64_t bk,
                    int64_t bn, int64_t M, int64_t N, int64_t K) {
     if (M == 0 || N == 0) return DN_OK;
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return set_error(DN_ERR_UNSUPPORTED, "MatMatDot: extent exceeds 2^31-1");
@@ -532,6 +558,108 @@ dn_status gemm_simt(T *c, int64_t cm, int64_t cn, const T *a, int64_t am, int64_
         DN_LAUNCH((gemm_simt_kernel<T>), grid, 256, 0, c, cm, cn, a, am, ak, b, bk, bn, (int)M, (int)N, (int)K, batch);
     }
     return launch_status("SIMT GEMM kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// float32 at fp32 accuracy (DN_MATH_FP32, the default): 3xTF32 on the tensor cores
+// ---------------------------------------------------------------------------------------------------------------
+std::atomic<int> g_math_mode{DN_MATH_FP32};
+
+__device__ __forceinline__ float to_tf32(float x) {  // round to nearest, ties away: the result is a tf32-exact fp32 word
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// hi = tf32(x), lo = tf32(x - hi) for a K-major [rows, K] operand (row pitch `rs` elements) into dense [rows, pitch]
+// arrays. Both outputs are exactly representable in tf32, so whatever the tensor core does with the low 13 bits of
+// its inputs (it ignores them) does not matter. Non-finite x: hi = x, lo = 0.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float *src, int64_t rs, int64_t rows, int64_t K, float *hi,
+                                                        float *lo, int64_t pitch) {
+    const int64_t n4 = pitch / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n4, k = (i - r * n4) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *row = src + r * rs;
+        if (k + 4 <= K) v = *reinterpret_cast<const float4 *>(row + k);
+        else {
+            if (k < K) v.x = row[k];
+            if (k + 1 < K) v.y = row[k + 1];
+            if (k + 2 < K) v.z = row[k + 2];
+        }
+        float4 h, l;
+        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+        l.x = isfinite(v.x) ? to_tf32(v.x - h.x) : 0.f;
+        l.y = isfinite(v.y) ? to_tf32(v.y - h.y) : 0.f;
+        l.z = isfinite(v.z) ? to_tf32(v.z - h.z) : 0.f;
+        l.w = isfinite(v.w) ? to_tf32(v.w - h.w) : 0.f;
+        *reinterpret_cast<float4 *>(hi + r * pitch + k) = h;
+        *reinterpret_cast<float4 *>(lo + r * pitch + k) = l;
+    }
+}
+
+// Makes `o` K-major (in place when it already is, else through the transposing copy) and splits it; on return
+// hi / lo are dense [rows, pitch] scratch arrays.
+dn_status split_operand(Operand2D o, float **hi, float **lo, int64_t *pitch, void **scratch_hi, void **scratch_lo) {
+    void *packed = nullptr;
+    dn_status st = DN_OK;
+    if (!tma_ready(o)) st = repack_kmajor(o, &packed);
+    *pitch = (o.K + 3) / 4 * 4;
+    if (st == DN_OK) st = scratch_alloc((size_t)o.rows * *pitch * 4, scratch_hi);
+    if (st == DN_OK) st = scratch_alloc((size_t)o.rows * *pitch * 4, scratch_lo);
+    if (st == DN_OK) {
+        *hi = static_cast<float *>(*scratch_hi);
+        *lo = static_cast<float *>(*scratch_lo);
+        int64_t ctas = (o.rows * (*pitch / 4) + 255) / 256;
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (ctas > cap) ctas = cap;
+        DN_LAUNCH(split_tf32_kernel, (unsigned)ctas, 256, 0, o.ptr, o.rs, o.rows, o.K, *hi, *lo, *pitch);
+        st = launch_status("tf32 split kernel");
+    }
+    scratch_free(packed);
+    return st;
+}
+
+dn_status gemm_f32_split(float *c, int64_t cm, int64_t cn, const float *a, int64_t am, int64_t ak, const float *b, int64_t bk,
+                         int64_t bn, int64_t M, int64_t N, int64_t K) {
+    Operand2D A{a, M, K, am, ak}, B{b, N, K, bn, bk};  // B viewed as [N, K]
+    float *ahi = nullptr, *alo = nullptr, *bhi = nullptr, *blo = nullptr;
+    int64_t pa = 0, pb = 0;
+    void *s0 = nullptr, *s1 = nullptr, *s2 = nullptr, *s3 = nullptr;
+    dn_status st = split_operand(A, &ahi, &alo, &pa, &s0, &s1);
+    if (st == DN_OK) st = split_operand(B, &bhi, &blo, &pb, &s2, &s3);
+    CUtensorMap ma, mb, mal, mbl;
+    GemmParams p;
+    p.c = c; p.ldc_m = cm; p.ldc_n = cn;
+    p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K;
+    const int BN = N <= 32 ? 32 : 128;
+    p.tiles_m = (int32_t)((M + kBM - 1) / kBM);
+    p.tiles_n = (int32_t)((N + BN - 1) / BN);
+    if (st == DN_OK) st = make_map(&ma, ahi, M, K, pa, kBM);
+    if (st == DN_OK) st = make_map(&mal, alo, M, K, pa, kBM);
+    if (st == DN_OK) st = make_map(&mb, bhi, N, K, pb, BN);
+    if (st == DN_OK) st = make_map(&mbl, blo, N, K, pb, BN);
+    if (st == DN_OK)
+        st = BN == 32 ? launch_tf32<32, false, false, true>(ma, mb, mal, mbl, p)
+                      : launch_tf32<128, false, false, true>(ma, mb, mal, mbl, p);
+    scratch_free(s0);
+    scratch_free(s1);
+    scratch_free(s2);
+    scratch_free(s3);
+    return st;
+}
+
+// MatMatDot on float32. DN_MATH_FP32 (default): the result has fp32 accuracy, like the reference's cuBLAS SGEMM
+// (its own test "Single matrix dot" compares with the host at rel 1e-5, Tensor.Test/CudaTests.fs:52-62) — small
+// problems on the exact fp32 SIMT kernel, large ones as 3xTF32 on the tensor cores. DN_MATH_TF32: one tf32 pass.
+dn_status gemm_f32(float *c, int64_t cm, int64_t cn, const float *a, int64_t am, int64_t ak, const float *b, int64_t bk,
+                   int64_t bn, int64_t M, int64_t N, int64_t K) {
+    if (g_math_mode.load(std::memory_order_relaxed) == DN_MATH_TF32 || M == 0 || N == 0 || K == 0)
+        return gemm_f32_tf32(c, cm, cn, a, am, ak, b, bk, bn, M, N, K);
+    if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return set_error(DN_ERR_UNSUPPORTED, "MatMatDot: extent exceeds 2^31-1");
+    if (M * N * K < ((int64_t)1 << 27))
+        return gemm_simt<float>(c, cm, cn, a, am, ak, b, bk, bn, M, N, K, 0, nullptr, nullptr, nullptr, nullptr);
+    return gemm_f32_split(c, cm, cn, a, am, ak, b, bk, bn, M, N, K);
 }
 
 dn_status gemm_f64(double *c, int64_t cm, int64_t cn, const double *a, int64_t am, int64_t ak, const double *b, int64_t bk,
@@ -754,6 +882,18 @@ dn_status matvec_t_run(const dn_tensor *t, const dn_tensor *a, const dn_tensor *
 }  // namespace
 
 extern "C" {
+
+dn_status dn_set_math_mode(int32_t mode) {
+    if (mode != DN_MATH_FP32 && mode != DN_MATH_TF32) return set_error(DN_ERR_INVALID_ARG, "dn_set_math_mode: bad mode %d", mode);
+    g_math_mode.store(mode, std::memory_order_relaxed);
+    return DN_OK;
+}
+
+dn_status dn_get_math_mode(int32_t *mode) {
+    if (!mode) return set_error(DN_ERR_INVALID_ARG, "dn_get_math_mode: null argument");
+    *mode = g_math_mode.load(std::memory_order_relaxed);
+    return DN_OK;
+}
 
 dn_status dn_mat_mat_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b) {
     dn_status st = check_mm(t, a, b, 2, "MatMatDot");

@@ -28,6 +28,17 @@ constexpr int64_t kCounterOff = 256, kCountsOff = 512;
 constexpr int64_t kScratchHalf = 8ll << 20;      // partials of reductions over the sharded axis (two halves)
 constexpr int64_t kHeapOff = kFlagBytes + 2 * kScratchHalf;
 
+// What still has to happen on a rank's stream after its signalling kernel: the wait half of the barrier and,
+// for some collectives, a step that needs every rank's contribution.
+struct PostJob {
+    int kind = 0;  // 0: none, 1: fold the per-rank partials of a sharded-axis reduction, 2: read the counts back
+    int red_kind = 0, op = 0, in_dt = 0, world = 0;
+    dn_tensor t = {};
+    char *half = nullptr;
+    int64_t slot_bytes = 0, n = 0;
+    int64_t *counts_dev = nullptr;
+};
+
 struct ShardRank {
     bool local = false;
     int device = -1;
@@ -39,19 +50,23 @@ struct ShardRank {
     uint32_t scratch_uses = 0;
     int64_t last_target = -1;   // window offset of the previous collective's target
     int64_t *host_counts = nullptr;  // pinned, kMaxShardRanks entries: read-back of dn_shard_count_true
+    bool has_pending = false;        // inside dn_shard_group_start / _end: the deferred wait + post job
+    PeerSync pending_sync = {};
+    PostJob pending_job;
 };
 
 struct ShardGroup {
     int world = 0;
     int64_t heap_bytes = 0, window_bytes = 0;
     bool connected = false;
+    bool grouping = false;  // between dn_shard_group_start and dn_shard_group_end
     ShardRank r[kMaxShardRanks];
 };
 
 // Binds the calling thread to a rank's device and stream for the duration of one call.
 struct RankScope {
     int prev_dev = 0;
-    void *prev_stream = nullptr;
+    cudaStream_t prev_stream = nullptr;
     bool switched = false;
     explicit RankScope(const ShardRank &r) {
         cudaGetDevice(&prev_dev);
@@ -59,11 +74,11 @@ struct RankScope {
             cudaSetDevice(r.device);
             switched = true;
         }
-        dn_get_stream(&prev_stream);
-        dn_set_stream(r.stream);
+        prev_stream = current_stream();
+        set_thread_stream(r.stream);
     }
     ~RankScope() {
-        dn_set_stream(prev_stream);
+        set_thread_stream(prev_stream);
         if (switched) cudaSetDevice(prev_dev);
     }
 };
@@ -139,21 +154,20 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const __grid_constant__ 
     peer_exit(ps);
 }
 
-dn_status launch_barrier(const PeerSync &ps) {
+// The SIGNAL half on its own (nothing to store, or a pure barrier).
+dn_status launch_signal(const PeerSync &ps) {
     DN_LAUNCH(peer_barrier_kernel, 1, 32, 0, ps);
-    dn_status st = launch_status("shard barrier kernel");
-    return st != DN_OK ? st : enqueue_wait(ps);
+    return launch_status("shard signal kernel");
 }
 
 dn_status launch_push(const PeerSync &ps, char *base, int64_t nbytes) {
-    if (nbytes <= 0 || ps.npeers == 0) return launch_barrier(ps);
+    if (nbytes <= 0 || ps.npeers == 0) return launch_signal(ps);
     int64_t ctas = (nbytes / 16 + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 4;
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
     DN_LAUNCH(peer_push_kernel, (unsigned)ctas, 256, 0, ps, base, nbytes);
-    dn_status st = launch_status("shard push kernel");
-    return st != DN_OK ? st : enqueue_wait(ps);
+    return launch_status("shard push kernel");
 }
 
 // Runs `body` (ordinary operator entry points) with `ps` pending; if no kernel consumed it (empty slab, nothing to
@@ -166,7 +180,28 @@ dn_status with_pending(const PeerSync &ps, F body) {
     const bool unconsumed = t_has_pending;
     t_has_pending = false;
     if (st != DN_OK) return st;
-    return unconsumed ? launch_barrier(ps) : enqueue_wait(ps);
+    return unconsumed ? launch_signal(ps) : DN_OK;
+}
+
+dn_status run_post(ShardRank &me, const PostJob &job);  // below, next to the fold kernels
+
+// The second half of every collective, on the rank's stream: hold the stream until every rank has signalled, then
+// run the step that needs all contributions. Inside a dn_shard_group_start / _end bracket (ONE thread driving
+// several ranks) this half is deferred to dn_shard_group_end, i.e. until every local rank has issued its signalling
+// kernel: a stream that is already waiting for a peer whose kernel the same thread has yet to launch would turn any
+// blocking call on the way there (a lazily loaded kernel, a pool that has to grow) into a deadlock — the reason
+// ncclGroupStart / ncclGroupEnd exist.
+dn_status complete(ShardGroup &g, ShardRank &me, const PeerSync &ps, const PostJob &job) {
+    if (g.grouping) {
+        if (me.has_pending)
+            return set_error(DN_ERR_INVALID_ARG, "one collective per rank between dn_shard_group_start and dn_shard_group_end");
+        me.has_pending = true;
+        me.pending_sync = ps;
+        me.pending_job = job;
+        return DN_OK;
+    }
+    dn_status st = enqueue_wait(ps);
+    return st != DN_OK ? st : run_post(me, job);
 }
 
 bool in_heap(const ShardGroup &g, const ShardRank &r, const char *p, int64_t nbytes) {
@@ -179,7 +214,12 @@ bool in_heap(const ShardGroup &g, const ShardRank &r, const char *p, int64_t nby
 dn_status guard_target(ShardGroup &g, ShardRank &me, int rank, const char *target) {
     const int64_t off = target - me.window;
     if (off == me.last_target) {
-        dn_status st = launch_barrier(make_sync(g, me, rank, false));
+        if (g.grouping)
+            return set_error(DN_ERR_INVALID_ARG, "the same target twice in a row inside a group bracket: issue "
+                                                 "dn_shard_barrier on every rank (its own bracket) in between");
+        const PeerSync ps = make_sync(g, me, rank, false);
+        dn_status st = launch_signal(ps);
+        if (st == DN_OK) st = enqueue_wait(ps);
         if (st != DN_OK) return st;
     }
     me.last_target = off;
@@ -452,7 +492,35 @@ dn_status dn_shard_barrier(void *group, int32_t rank) {
     if (st != DN_OK) return st;
     RankScope scope(*me);
     me->last_target = -1;
-    return launch_barrier(make_sync(*g, *me, rank, false));
+    const PeerSync ps = make_sync(*g, *me, rank, false);
+    if ((st = launch_signal(ps)) != DN_OK) return st;
+    return complete(*g, *me, ps, PostJob());
+}
+
+// One thread driving several ranks brackets each collective: start; the call on every local rank; end.
+dn_status dn_shard_group_start(void *group) {
+    ShardGroup *g = static_cast<ShardGroup *>(group);
+    if (!g || !g->connected) return set_error(DN_ERR_INVALID_ARG, "dn_shard_group_start: bad group");
+    if (g->grouping) return set_error(DN_ERR_INVALID_ARG, "dn_shard_group_start: brackets do not nest");
+    g->grouping = true;
+    return DN_OK;
+}
+
+dn_status dn_shard_group_end(void *group) {
+    ShardGroup *g = static_cast<ShardGroup *>(group);
+    if (!g || !g->grouping) return set_error(DN_ERR_INVALID_ARG, "dn_shard_group_end without dn_shard_group_start");
+    g->grouping = false;
+    dn_status first = DN_OK;
+    for (int k = 0; k < g->world; ++k) {
+        ShardRank &r = g->r[k];
+        if (!r.local || !r.has_pending) continue;
+        r.has_pending = false;
+        RankScope scope(r);
+        dn_status st = enqueue_wait(r.pending_sync);
+        if (st == DN_OK) st = run_post(r, r.pending_job);
+        if (st != DN_OK && first == DN_OK) first = st;
+    }
+    return first;
 }
 
 // ---- reductions over a non-sharded axis: one launch per rank, direct peer stores ------------------------------
@@ -471,7 +539,8 @@ static dn_status shard_rows_op(void *group, int32_t rank, const dn_tensor *t_ful
     RankScope scope(*me);
     if ((st = guard_target(*g, *me, rank, data_ptr(t_full))) != DN_OK) return st;
     const PeerSync ps = make_sync(*g, *me, rank, true);
-    return with_pending(ps, [&] { return run(&mine, a_local, ctx); });
+    if ((st = with_pending(ps, [&] { return run(&mine, a_local, ctx); })) != DN_OK) return st;
+    return complete(*g, *me, ps, PostJob());
 }
 
 dn_status dn_shard_reduce_last_axis(void *group, int32_t rank, int32_t op, const dn_tensor *t_full,
@@ -537,7 +606,8 @@ dn_status dn_shard_minmax_arg_last_axis(void *group, int32_t rank, int32_t op, c
     RankScope scope(*me);
     if ((st = guard_target(*g, *me, rank, data_ptr(t_val_full))) != DN_OK) return st;
     const PeerSync ps = make_sync(*g, *me, rank, true);
-    return with_pending(ps, [&] { return minmax_arg_local(op, &mv, &mi, a_local); });
+    if ((st = with_pending(ps, [&] { return minmax_arg_local(op, &mv, &mi, a_local); })) != DN_OK) return st;
+    return complete(*g, *me, ps, PostJob());
 }
 
 dn_status dn_shard_all_gather_rows(void *group, int32_t rank, const dn_tensor *t_full, int64_t row_begin,
@@ -553,7 +623,9 @@ dn_status dn_shard_all_gather_rows(void *group, int32_t rank, const dn_tensor *t
     if ((st = slab_view(mine, t_full, row_begin, nrows, what)) != DN_OK) return st;
     RankScope scope(*me);
     me->last_target = data_ptr(t_full) - me->window;
-    return launch_push(make_sync(*g, *me, rank, true), data_ptr(&mine), num_elements(&mine) * dtype_size(mine.dtype));
+    const PeerSync ps = make_sync(*g, *me, rank, true);
+    if ((st = launch_push(ps, data_ptr(&mine), num_elements(&mine) * dtype_size(mine.dtype))) != DN_OK) return st;
+    return complete(*g, *me, ps, PostJob());
 }
 
 }  // extern "C"
@@ -774,21 +846,52 @@ dn_status dn_shard_reduce_sharded_axis(void *group, int32_t rank, int32_t kind, 
         }
     }
     if (st != DN_OK) return st;
-    // 2. replicate the slot into every rank's scratch; exit barrier
+    // 2. replicate the slot into every rank's scratch and signal; 3. (after the wait) fold the W partials locally
     me->last_target = -1;
-    if ((st = launch_push(make_sync(*g, *me, rank, true), slot, n * elem)) != DN_OK) return st;
-    // 3. local fold of the W partials in rank order (identical bits on every rank)
-    if (kind == 0) {
+    const PeerSync ps = make_sync(*g, *me, rank, true);
+    if ((st = launch_push(ps, slot, n * elem)) != DN_OK) return st;
+    PostJob job;
+    job.kind = 1;
+    job.red_kind = kind;
+    job.op = op;
+    job.in_dt = in_dt;
+    job.world = W;
+    job.t = *t;
+    job.half = half;
+    job.slot_bytes = slot_bytes;
+    job.n = n;
+    return complete(*g, *me, ps, job);
+}
+
+}  // extern "C"
+
+namespace dn {
+namespace {
+
+// Runs on the rank's stream (RankScope active) after the wait.
+dn_status run_post(ShardRank &me, const PostJob &job) {
+    if (job.kind == 2) {
+        DN_CUDA_TRY(cudaMemcpyAsync(me.host_counts, job.counts_dev, sizeof(int64_t) * job.world, cudaMemcpyDeviceToHost,
+                                    current_stream()));
+        return DN_OK;
+    }
+    if (job.kind != 1) return DN_OK;
+    // local fold of the W partials in rank order (identical bits on every rank)
+    const dn_tensor *t = &job.t;
+    const char *half = job.half;
+    const int64_t slot_bytes = job.slot_bytes, n = job.n;
+    const int W = job.world, op = job.op;
+    if (job.red_kind == 0) {
         if (op == DN_COUNT_TRUE) return launch_fold<SumOp<int64_t>, kFoldValue>(t, half, slot_bytes, W, n);
         if (op == DN_ALL) return launch_fold<AllAnyOp<true>, kFoldValue>(t, half, slot_bytes, W, n);
         if (op == DN_ANY) return launch_fold<AllAnyOp<false>, kFoldValue>(t, half, slot_bytes, W, n);
-        DN_SWITCH_DTYPE(in_dt, {
+        DN_SWITCH_DTYPE(job.in_dt, {
             if constexpr (!kIsBool<T>) return fold_value<T>(op, t, half, slot_bytes, W, n);
         });
         return DN_OK;
     }
-    if (kind == 1) {
-        DN_SWITCH_DTYPE(in_dt, {
+    if (job.red_kind == 1) {
+        DN_SWITCH_DTYPE(job.in_dt, {
             if constexpr (!kIsBool<T>) {
                 if (op == DN_ARG_MAX) return launch_fold<ArgOp<T, true>, kFoldArg>(t, half, slot_bytes, W, n);
                 return launch_fold<ArgOp<T, false>, kFoldArg>(t, half, slot_bytes, W, n);
@@ -798,6 +901,11 @@ dn_status dn_shard_reduce_sharded_axis(void *group, int32_t rank, int32_t kind, 
     }
     return launch_fold<FindOp<int64_t>, kFoldFind>(t, half, slot_bytes, W, n);
 }
+
+}  // namespace
+}  // namespace dn
+
+extern "C" {
 
 // ---- ordered compaction over the shards (row-major order of the full tensor == rank order of the slabs) ----------
 dn_status dn_shard_count_true_begin(void *group, int32_t rank, const dn_tensor *mask_local) {
@@ -811,10 +919,13 @@ dn_status dn_shard_count_true_begin(void *group, int32_t rank, const dn_tensor *
     int64_t *slot = reinterpret_cast<int64_t *>(me->window + kCountsOff) + (me->scratch_uses++ & 1) * kMaxShardRanks;
     if ((st = count_true_async(mask_local, reinterpret_cast<unsigned long long *>(slot + rank))) != DN_OK) return st;
     me->last_target = -1;
-    if ((st = launch_push(make_sync(*g, *me, rank, true), reinterpret_cast<char *>(slot + rank), sizeof(int64_t))) != DN_OK)
-        return st;
-    DN_CUDA_TRY(cudaMemcpyAsync(me->host_counts, slot, sizeof(int64_t) * g->world, cudaMemcpyDeviceToHost, me->stream));
-    return DN_OK;
+    const PeerSync ps = make_sync(*g, *me, rank, true);
+    if ((st = launch_push(ps, reinterpret_cast<char *>(slot + rank), sizeof(int64_t))) != DN_OK) return st;
+    PostJob job;
+    job.kind = 2;
+    job.world = g->world;
+    job.counts_dev = slot;
+    return complete(*g, *me, ps, job);
 }
 
 dn_status dn_shard_count_true_end(void *group, int32_t rank, int64_t *counts) {
@@ -855,7 +966,9 @@ dn_status dn_shard_true_indices(void *group, int32_t rank, const dn_tensor *t_fu
             if ((st = launch_status("shard column shift kernel")) != DN_OK) return st;
         }
     }
-    return launch_push(make_sync(*g, *me, rank, true), data_ptr(&mine), nrows_local * t_full->shape[1] * 8);
+    const PeerSync ps = make_sync(*g, *me, rank, true);
+    if ((st = launch_push(ps, data_ptr(&mine), nrows_local * t_full->shape[1] * 8)) != DN_OK) return st;
+    return complete(*g, *me, ps, PostJob());
 }
 
 dn_status dn_shard_masked_get(void *group, int32_t rank, const dn_tensor *t_full, int64_t elem_offset,
@@ -909,7 +1022,9 @@ dn_status dn_shard_masked_get(void *group, int32_t rank, const dn_tensor *t_full
         scratch_free(tmp_m);
         if (st != DN_OK) return st;
     }
-    return launch_push(make_sync(*g, *me, rank, true), data_ptr(&mine), nelems_local * dtype_size(t_full->dtype));
+    const PeerSync ps = make_sync(*g, *me, rank, true);
+    if ((st = launch_push(ps, data_ptr(&mine), nelems_local * dtype_size(t_full->dtype))) != DN_OK) return st;
+    return complete(*g, *me, ps, PostJob());
 }
 
 }  // extern "C"

@@ -56,6 +56,9 @@ dn_status cuda_error(cudaError_t err, const char *what) {
 }
 
 cudaStream_t current_stream() { return t_stream; }
+// Library-internal switch of the calling thread's stream (shard.cu binds a rank's stream for the duration of a call):
+// unlike dn_set_stream it does not enter the stream into the device's list of streams that storage releases fence.
+void set_thread_stream(cudaStream_t s) { t_stream = s; }
 bool check_errors_enabled() { return t_check_errors != 0; }
 
 static DeviceState *device_state() {
@@ -72,6 +75,13 @@ static DeviceState *device_state() {
             if (e == cudaSuccess) {
                 uint64_t threshold = UINT64_MAX;  // keep freed blocks cached in the pool
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+                // A block freed on stream A may be handed to stream B only once the free has completed (or an
+                // event dependency between the streams already exists) — never by making B wait on A behind the
+                // caller's back. Hidden cross-stream dependencies would serialise the per-thread streams the
+                // reference's threading model relies on (CudaCfg.fs:25-27) and deadlock ranks that share a device
+                // (dn_shard_*: rank A's stream waits for a signal that rank B's kernel has yet to send).
+                int off = 0;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
             }
         }
         if (e == cudaSuccess) e = cudaMalloc((void **)&s.index_error, sizeof(int));

@@ -129,6 +129,8 @@ _DEVICE_SIGNATURES = {
     "poll_index_error": [C.POINTER(C.c_int32)],
     "alloc": [C.c_int64, C.POINTER(C.c_void_p)],
     "free": [C.c_void_p],
+    "set_math_mode": [C.c_int32],
+    "get_math_mode": [C.POINTER(C.c_int32)],
     "free_deferred": [C.c_void_p],
     "release_stream": [C.c_void_p],
     "host_register": [C.c_void_p, C.c_int64],
@@ -161,6 +163,8 @@ _DEVICE_SIGNATURES = {
     "shard_heap_alloc": [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)],
     "shard_heap_reset": [C.c_void_p, C.c_int32],
     "shard_barrier": [C.c_void_p, C.c_int32],
+    "shard_group_start": [C.c_void_p],
+    "shard_group_end": [C.c_void_p],
     "shard_reduce_last_axis": [C.c_void_p, C.c_int32, C.c_int32, _P, C.c_int64, _P],
     "shard_arg_reduce_last_axis": [C.c_void_p, C.c_int32, C.c_int32, _P, C.c_int64, _P],
     "shard_find_last_axis": [C.c_void_p, C.c_int32, C.c_void_p, _P, C.c_int64, _P],

@@ -12,11 +12,14 @@ no torch.distributed. Two process models:
     [bytes] * world` is any all-gather of 64-byte blobs the harness has (torch.distributed, MPI, files ...). It is
     used once, for the window handles.
 
-Sharded results are allocated from the group's symmetric heap (`alloc`); all calls are collective.
+Sharded results are allocated from the group's symmetric heap (`alloc`); all calls are collective. A thread that
+drives several ranks issues each collective on all of them inside `with group.bracket():` (dn_shard_group_start /
+dn_shard_group_end — the ncclGroupStart / ncclGroupEnd of this library).
 """
 from __future__ import annotations
 
 import ctypes as C
+from contextlib import contextmanager
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 from . import dtypes, native
@@ -85,9 +88,23 @@ class ShardGroup:
         for r in (self.ranks if rank is None else [rank]):
             self.api.call("shard_sync", self._g, r)
 
+    @contextmanager
+    def bracket(self):
+        """dn_shard_group_start / dn_shard_group_end around ONE collective issued on every local rank by this thread.
+        A no-op when this process drives a single rank (every call then completes its own wait)."""
+        if len(self.ranks) > 1:
+            self.api.call("shard_group_start", self._g)
+            try:
+                yield
+            finally:
+                self.api.call("shard_group_end", self._g)
+        else:
+            yield
+
     def barrier(self) -> None:
-        for r in self.ranks:
-            self.api.call("shard_barrier", self._g, r)
+        with self.bracket():
+            for r in self.ranks:
+                self.api.call("shard_barrier", self._g, r)
 
     def heap_reset(self) -> None:
         for r in self.ranks:
@@ -162,8 +179,9 @@ class ShardGroup:
     # -- ordered compaction (row-major order of the full tensor == rank order of the slabs) ------------------------
     def count_true(self, masks: Dict[int, Tensor]) -> List[int]:
         """counts[r] = number of true elements of rank r's mask slab (blocking). `masks`: local rank -> slab."""
-        for r in self.ranks:
-            self.api.call("shard_count_true_begin", self._g, r, self._d(masks[r]))
+        with self.bracket():
+            for r in self.ranks:
+                self.api.call("shard_count_true_begin", self._g, r, self._d(masks[r]))
         counts = (C.c_int64 * self.world)()
         for r in self.ranks:
             self.api.call("shard_count_true_end", self._g, r, counts)
@@ -174,11 +192,12 @@ class ShardGroup:
         counts = self.count_true(masks)
         total = sum(counts)
         out = {}
-        for r in self.ranks:
-            m = masks[r]
-            out[r] = self.alloc(r, (total, m.NDims), dtypes.DN_I64)
-            self.api.call("shard_true_indices", self._g, r, self._d(out[r]), sum(counts[:r]), counts[r], self._d(m),
-                          row_begins[r])
+        with self.bracket():
+            for r in self.ranks:
+                m = masks[r]
+                out[r] = self.alloc(r, (total, m.NDims), dtypes.DN_I64)
+                self.api.call("shard_true_indices", self._g, r, self._d(out[r]), sum(counts[:r]), counts[r], self._d(m),
+                              row_begins[r])
         return out
 
     def masked_get(self, locals_: Dict[int, Tensor], masks: Dict[int, Tensor]) -> Dict[int, Tensor]:
@@ -186,9 +205,10 @@ class ShardGroup:
         counts = self.count_true(masks)
         total = sum(counts)
         out = {}
-        for r in self.ranks:
-            a = locals_[r]
-            out[r] = self.alloc(r, (total,), a.DataType)
-            self.api.call("shard_masked_get", self._g, r, self._d(out[r]), sum(counts[:r]), counts[r], self._d(a),
-                          self._d(masks[r]))
+        with self.bracket():
+            for r in self.ranks:
+                a = locals_[r]
+                out[r] = self.alloc(r, (total,), a.DataType)
+                self.api.call("shard_masked_get", self._g, r, self._d(out[r]), sum(counts[:r]), counts[r], self._d(a),
+                              self._d(masks[r]))
         return out

@@ -10,6 +10,7 @@ open System.Runtime.InteropServices
 open Tensor
 open Tensor.Utils
 open Tensor.Backend
+open Tensor.Host
 
 module internal Marshalling =
     let dtypeOf (t: Type) =
@@ -37,12 +38,86 @@ module internal Marshalling =
                                  else box value), GCHandleType.Pinned)
         try f (h.AddrOfPinnedObject ()) finally h.Free ()
 
+/// Index / mask tensor lists (Gather, Scatter, MaskedGet, MaskedSet): `const dn_tensor *const *` with NULL for
+/// None / NoMask. Replaces the Reflection.Emit'ed NativeIdxTensors struct (NativeTensor.fs:157-208,
+/// Kernels/GatherScatter.cuh:9-19): the descriptors are written to unmanaged memory for the duration of the call
+/// (DnTensor carries by-value arrays, so it is marshalled, not pinned) and passed as an array of pointers.
+module internal B200Index =
+    let private descSize = Marshal.SizeOf typeof<DnTensor>
+
+    /// Runs `f ptrs` with ptrs.[i] = pointer to a native copy of the i-th descriptor, IntPtr.Zero for None.
+    let private withDescs (descs: DnTensor option list) (f: nativeint[] -> DnStatus) =
+        let n = List.length descs
+        let block = Marshal.AllocHGlobal (max 1 n * descSize)
+        try
+            let ptrs =
+                descs |> List.mapi (fun i d ->
+                    match d with
+                    | Some d -> let p = block + nativeint (i * descSize)
+                                Marshal.StructureToPtr (d, p, false)
+                                p
+                    | None -> IntPtr.Zero)
+                |> Array.ofList
+            Native.check (f (if n = 0 then [| IntPtr.Zero |] else ptrs))
+        finally Marshal.FreeHGlobal block
+
+    let gather (trgt: DnTensor) (idxs: DnTensor option list) (src: DnTensor) =
+        let mutable t, a = trgt, src
+        withDescs idxs (fun p -> Native.dn_gather (&t, p, List.length idxs, &a))
+    let scatter (trgt: DnTensor) (idxs: DnTensor option list) (src: DnTensor) =
+        let mutable t, a = trgt, src
+        withDescs idxs (fun p -> Native.dn_scatter (&t, p, List.length idxs, &a))
+    let maskedGet (trgt: DnTensor) (src: DnTensor) (masks: DnTensor option []) =
+        let mutable t, a = trgt, src
+        withDescs (List.ofArray masks) (fun p -> Native.dn_masked_get (&t, &a, p, masks.Length))
+    let maskedSet (trgt: DnTensor) (masks: DnTensor option []) (src: DnTensor) =
+        let mutable t, a = trgt, src
+        withDescs (List.ofArray masks) (fun p -> Native.dn_masked_set (&t, p, masks.Length, &a))
+
+/// Host <-> device Transfer (CudaBackend.fs:206-270). The managed array is pinned for the duration of the call and
+/// registered with CUDA when possible (CudaRegMem.fs:114-146; DN_ERR_INVALID_ARG = the reference's
+/// CannotCudaRegisterMemoryException: fall back to plain pinning). Any pair of layouts goes through in ONE native
+/// call: dn_transfer_h2d / dn_transfer_d2h do the strided packing and the on-device layout change that the
+/// reference does with `src.Copy(order=RowMajor)` on the host and a temporary device tensor + CopyFrom.
+module internal B200Transfer =
+    let private withHostMem (hs: ITensorHostStorage) (f: nativeint -> unit) =
+        use pin = hs.Pin ()
+        let registered = Native.dn_host_register (pin.Ptr, hs.DataSizeInBytes) = DnStatus.Ok
+        try f pin.Ptr
+        finally
+            // the copy may still be in flight on the thread's stream: the array must stay pinned until it has left
+            // (the reference defers the unpin with a stream callback, CudaBackend.fs:232,252)
+            Native.check (Native.dn_sync ())
+            if registered then Native.dn_host_unregister pin.Ptr |> ignore
+
+    let hostToDevice (devDesc: DnTensor) (hs: ITensorHostStorage) (hostLayout: TensorLayout) (dtype: DnDType) =
+        withHostMem hs (fun p ->
+            let mutable d, h = devDesc, Marshalling.desc p hostLayout dtype
+            Native.check (Native.dn_transfer_h2d (&d, &h)))
+
+    let deviceToHost (hs: ITensorHostStorage) (hostLayout: TensorLayout) (devDesc: DnTensor) (dtype: DnDType) =
+        withHostMem hs (fun p ->
+            let mutable h, d = Marshalling.desc p hostLayout dtype, devDesc
+            Native.check (Native.dn_transfer_d2h (&h, &d)))
+
 type TensorB200Storage<'T when 'T: (new: unit -> 'T) and 'T: struct and 'T :> ValueType> (nElems: int64) =
     let nElems = max nElems 1L                                   // CudaBackend.fs:56-58
     let mutable ptr = 0n
     do Native.check (Native.dn_alloc (nElems * sizeof64<'T>, &ptr))
     member this.Ptr = ptr
-    override this.Finalize () = if ptr <> 0n then Native.dn_free ptr |> ignore   // stream-ordered free
+    /// Explicit release from the thread that used the storage: stream-ordered (dn_free).
+    member this.Dispose () =
+        if ptr <> 0n then
+            Native.dn_free ptr |> ignore
+            ptr <- 0n
+            GC.SuppressFinalize this
+    /// The finalizer thread owns no stream and may not even have the storage's device current: the release is only
+    /// QUEUED on the owning device (dn_free_deferred) and carried out by the next dn_alloc / dn_sync of a thread that
+    /// works there, behind a fence over the device's streams (the reference: CudaBackend.fs:73-74 + the
+    /// keep-alive events of CudaUtils.fs:122-177).
+    override this.Finalize () = if ptr <> 0n then Native.dn_free_deferred ptr |> ignore
+    interface IDisposable with
+        member this.Dispose () = this.Dispose ()
     interface ITensorStorage<'T> with
         member this.Backend layout = TensorB200Backend<'T> (layout, this) :> ITensorBackend<_>
         member this.Dev = TensorB200Device.Instance :> ITensorDevice
@@ -77,7 +152,13 @@ and TensorB200Backend<'T when 'T: (new: unit -> 'T) and 'T: struct and 'T :> Val
                 Native.check (Native.dn_fill_incrementing (&t, s, i))))
         member this.Copy (trgt, src) = let mutable t, a = d trgt, d src in Native.check (Native.dn_copy (&t, &a))
         member this.Convert (trgt, src) = let mutable t, a = d trgt, d src in Native.check (Native.dn_convert (&t, &a))
-        member this.Transfer (trgt, src) = B200Transfer.transfer trgt src     // dn_memcpy_h2d / dn_memcpy_d2h
+        member this.Transfer (trgt, src) =
+            match trgt.Storage, src.Storage with
+            | (:? TensorB200Storage<'T>), (:? TensorHostStorage<'T> as hs) ->
+                B200Transfer.hostToDevice (d trgt) (hs :> ITensorHostStorage) src.Layout dt; true
+            | (:? TensorHostStorage<'T> as hs), (:? TensorB200Storage<'T>) ->
+                B200Transfer.deviceToHost (hs :> ITensorHostStorage) trgt.Layout (d src) dt; true
+            | _ -> false
         // unary: op codes are dn_unary_op
         member this.UnaryPlus (t, a) = unary 0 t a
         member this.UnaryMinus (t, a) = unary 1 t a
@@ -162,3 +243,20 @@ and TensorB200Device private () =
     override this.Id = "Cuda"                                     // same device id: existing code keeps working
     override this.Create nElems = TensorB200Storage<'T> nElems :> ITensorStorage<'T>
     override this.Zeroed = false
+
+/// Frontend helpers: the analogue of module CudaTensor (Tensor/Tensor/Cuda/CudaFrontend.fs:34-150).
+module B200Tensor =
+    /// The B200 device; `Tensor<'T>` code written against CudaTensor.Dev runs unchanged against it.
+    let Dev = TensorB200Device.Instance :> ITensorDevice
+    let transfer x = Tensor.transfer Dev x
+    let empty<'T> = Tensor<'T>.empty Dev
+    let zeros<'T> = Tensor<'T>.zeros Dev
+    let ones<'T> = Tensor<'T>.ones Dev
+    let filled<'T> = Tensor<'T>.filled Dev
+    let scalar<'T> = Tensor<'T>.scalar Dev
+    let counting = Tensor.counting Dev
+    /// Cfg.Stream (CudaCfg.fs:25-27): the calling thread's stream.
+    let setStream (stream: nativeint) = Native.check (Native.dn_set_stream stream)
+    /// Cfg.Stacktrace (CudaCfg.fs:33-35).
+    let setStacktrace (enabled: bool) = Native.check (Native.dn_set_check_errors (if enabled then 1 else 0))
+    let synchronize () = Native.check (Native.dn_sync ())

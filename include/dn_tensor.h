@@ -248,6 +248,15 @@ dn_status dn_true_indices(const dn_tensor *t, const dn_tensor *a);
 /* ---------------------------------------------------------------------------------------------------------------
  * Dense contractions.  f32 / f64.
  * ------------------------------------------------------------------------------------------------------------- */
+/* Precision of float32 MatMatDot / BatchedMatMatDot (process-wide). The reference calls cuBLAS SGEMM (full fp32;
+ * its test "Single matrix dot", Tensor.Test/CudaTests.fs:52-62, compares with the host at rel 1e-5).
+ *   DN_MATH_FP32 (default): fp32-accurate — small problems on an exact fp32 kernel, large ones as 3xTF32 on the
+ *                           tensor cores (operands split into two tf32 halves, three tcgen05 MMAs per k-step);
+ *   DN_MATH_TF32          : one tcgen05 pass with tf32 inputs (10-bit mantissa), fp32 accumulation; rel 1e-2 of
+ *                           the fp64 result (BASELINE.json north_star), three times the throughput. Opt-in. */
+typedef enum dn_math_mode { DN_MATH_FP32 = 0, DN_MATH_TF32 = 1 } dn_math_mode;
+dn_status dn_set_math_mode(int32_t mode);
+dn_status dn_get_math_mode(int32_t *mode);
 /* VecVecDot / MatVecDot (TensorBackend.fs:137-138; CudaBackend.fs:383-408). */
 dn_status dn_vec_vec_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b);
 dn_status dn_mat_vec_dot(const dn_tensor *t, const dn_tensor *a, const dn_tensor *b);
@@ -280,7 +289,8 @@ dn_status dn_batched_invert(const dn_tensor *t, const dn_tensor *a);
  * (torchrun: nlocal == 1; the 64-byte window handles are exchanged by the host through any side channel).
  * Ranks may share a device (tests on a single GPU). Calls on one rank must come from one thread at a time and are
  * COLLECTIVE: every rank issues the same sequence of dn_shard_* operator calls. A result buffer may be reused as
- * the target of a later collective only after at least one other collective (or dn_shard_barrier) in between.
+ * the target of a later collective only after at least one other collective (or dn_shard_barrier) in between; the
+ * library inserts that barrier itself when the same target comes twice in a row (outside group brackets).
  * All dn_shard_* calls run on the rank's stream (dn_shard_set_stream; default: a stream owned by the group) and
  * leave the calling thread's current device and stream unchanged.
  * ------------------------------------------------------------------------------------------------------------- */
@@ -305,6 +315,15 @@ dn_status dn_shard_heap_alloc(void *group, int32_t rank, int64_t nbytes, void **
 dn_status dn_shard_heap_reset(void *group, int32_t rank);
 /* Flag barrier over peer memory on the ranks' streams (one tiny kernel per rank). */
 dn_status dn_shard_barrier(void *group, int32_t rank);
+/* ONE thread driving several ranks brackets every collective (as with ncclGroupStart / ncclGroupEnd):
+ *     dn_shard_group_start(g);  for each local rank r: dn_shard_<op>(g, r, ...);  dn_shard_group_end(g);
+ * Inside the bracket a call launches the rank's kernel (stores + signal) at once and defers the wait half of the
+ * barrier — and whatever needs every rank's contribution — to dn_shard_group_end, when every local rank has issued:
+ * a stream already waiting for a peer whose kernel the same thread has yet to launch would turn any blocking call on
+ * the way there into a deadlock. One collective per rank per bracket. Not needed (and not wanted) with one thread or
+ * one process per rank: there every call completes its own wait. */
+dn_status dn_shard_group_start(void *group);
+dn_status dn_shard_group_end(void *group);
 
 /* Reductions over an axis OTHER than the sharded one (every output row lives on one rank). a_local: this rank's
  * slab [rows_local, ..., L]; t_full: the FULL result [rows_total, ...] in the symmetric heap; the rank computes rows

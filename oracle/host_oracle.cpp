@@ -45,6 +45,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <omp.h>
 #include <limits>
 #include <type_traits>
 #include <vector>
@@ -478,6 +479,10 @@ extern "C" {
 
 const char *dno_last_error(void) { return g_err; }
 void dno_set_threads_enabled(int enabled) { g_threads_enabled = enabled; }
+// Number of worker threads of the Parallel.For restatement (0 = one per core). Launchers such as torchrun export
+// OMP_NUM_THREADS=1; the CPU arm of bench.py overrides that so that it runs on all cores whatever started it.
+void dno_set_num_threads(int n) { omp_set_num_threads(n > 0 ? n : omp_get_num_procs()); }
+int dno_get_num_threads(void) { return omp_get_max_threads(); }
 
 // HostBackend.FillConst (HostBackend.fs:187-190) -> VectorOps.Fill / ScalarOps.Fill (ScalarOps.fs:363-365).
 dn_status dno_fill_const(const dn_tensor *t, const void *value) {

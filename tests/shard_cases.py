@@ -61,9 +61,10 @@ def run(grp: ShardGroup, set_device) -> list:
 
     def collect(name, fn, want, rtol=0.0):
         outs = {}
-        for r in grp.ranks:
-            set_device(r)
-            outs[r] = fn(r)
+        with grp.bracket():
+            for r in grp.ranks:
+                set_device(r)
+                outs[r] = fn(r)
         if os.environ.get("DN_SHARD_DEBUG"):
             grp.sync()
             print("done:", name, flush=True)
@@ -107,26 +108,33 @@ def run(grp: ShardGroup, set_device) -> list:
     collect("f32 MaxLastAxis of a reversed slice",
             lambda r: grp.reduce_axis(r, "MaxLastAxis", loc[r]["f"][:, 10:].reverseAxis(1), 1, R, loc[r]["beg"]),
             hf[:, 10:].reverseAxis(1).maxAxis(1))
-    # the same target twice in a row: the library inserts the entry barrier
+    # the same target twice in a row: one rank per process -> the library inserts the entry barrier itself; one
+    # thread driving several ranks -> an explicit barrier bracket in between (the library refuses otherwise)
     reuse = {}
     for rep in range(2):
-        for r in grp.ranks:
-            set_device(r)
-            if r not in reuse:
-                reuse[r] = grp.alloc(r, (R,), dtypes.DN_I64)
-            grp.reduce_axis(r, "ArgMaxLastAxis" if rep else "ArgMinLastAxis", loc[r]["i"], 1, R, loc[r]["beg"], out=reuse[r])
+        if rep and len(grp.ranks) > 1:
+            grp.barrier()
+        with grp.bracket():
+            for r in grp.ranks:
+                set_device(r)
+                if r not in reuse:
+                    reuse[r] = grp.alloc(r, (R,), dtypes.DN_I64)
+                grp.reduce_axis(r, "ArgMaxLastAxis" if rep else "ArgMinLastAxis", loc[r]["i"], 1, R, loc[r]["beg"],
+                                out=reuse[r])
     results.append(("same target twice", reuse, hi.argMaxAxis(1).toNumpy(), 0.0))
     # Max + ArgMax in one pass
     fused_v, fused_i = {}, {}
-    for r in grp.ranks:
-        set_device(r)
-        fused_v[r], fused_i[r] = grp.minmax_arg(r, True, loc[r]["f"], R, loc[r]["beg"])
+    with grp.bracket():
+        for r in grp.ranks:
+            set_device(r)
+            fused_v[r], fused_i[r] = grp.minmax_arg(r, True, loc[r]["f"], R, loc[r]["beg"])
     results.append(("fused Max", fused_v, hf.maxAxis(1).toNumpy(), 0.0))
     results.append(("fused ArgMax", fused_i, hf.argMaxAxis(1).toNumpy(), 0.0))
     fused_v2, fused_i2 = {}, {}
-    for r in grp.ranks:
-        set_device(r)
-        fused_v2[r], fused_i2[r] = grp.minmax_arg(r, False, loc[r]["f"], R, loc[r]["beg"])
+    with grp.bracket():
+        for r in grp.ranks:
+            set_device(r)
+            fused_v2[r], fused_i2[r] = grp.minmax_arg(r, False, loc[r]["f"], R, loc[r]["beg"])
     results.append(("fused Min", fused_v2, hf.minAxis(1).toNumpy(), 0.0))
     results.append(("fused ArgMin", fused_i2, hf.argMinAxis(1).toNumpy(), 0.0))
     # ordered compaction across the shards

@@ -79,3 +79,72 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".in")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "host_oracle" not in text and "oracle." not in text.replace("oracle/", ""), f
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The F# P/Invoke binding (fsharp/Tensor.B200/Native.fs) cannot be compiled in this image (no dotnet); what can be
+# checked without a compiler is checked here: every extern names an exported symbol, every declared entry point has
+# an extern, and each pair agrees in arity and in the ABI class (pointer / int32 / int64) of every argument and of
+# the return value — the properties a wrong P/Invoke signature would break.
+# ---------------------------------------------------------------------------------------------------------------
+def _c_prototypes():
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"(dn_status|const char \*|int64_t)\s*(dn_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        def cls(a):
+            a = a.strip()
+            if "*" in a:
+                return "ptr"
+            if a.startswith("int32_t"):
+                return "i32"
+            if a.startswith("int64_t"):
+                return "i64"
+            raise AssertionError(f"{name}: unclassified C parameter {a!r}")
+        params = [] if args.strip() in ("", "void") else [cls(a) for a in args.split(",")]
+        protos[name] = ({"dn_status": "i32", "const char *": "ptr", "int64_t": "i64"}[ret], params)
+    return protos
+
+
+def _fsharp_externs():
+    text = open(os.path.join(ROOT, "fsharp", "Tensor.B200", "Native.fs")).read()
+    text = re.sub(r"//.*", "", text)
+    externs = {}
+    for ret, name, args in re.findall(r"extern\s+(\w+)\s+(dn_[a-z0-9_]+)\s*\(([^)]*)\)", text):
+        def cls(a):
+            ty = a.strip().rsplit(" ", 1)[0].strip()
+            if "&" in ty or "[]" in ty or ty == "nativeint":
+                return "ptr"
+            return {"int": "i32", "int32": "i32", "int64": "i64"}[ty]
+        params = [] if not args.strip() else [cls(a) for a in args.split(",")]
+        externs[name] = ({"DnStatus": "i32", "nativeint": "ptr", "int64": "i64"}[ret], params)
+    return externs
+
+
+def test_fsharp_externs_match_the_header_and_the_library():
+    api = native.product()
+    protos, externs = _c_prototypes(), _fsharp_externs()
+    assert len(protos) >= 70 and set(protos) == set(declared_symbols())
+    assert sorted(set(protos) - set(externs)) == [], "declared in dn_tensor.h but not bound in Native.fs"
+    assert sorted(set(externs) - set(protos)) == [], "bound in Native.fs but not declared in dn_tensor.h"
+    for name, sig in externs.items():
+        assert hasattr(api.lib, name), f"{name} is bound in Native.fs but not exported"
+        assert sig == protos[name], f"{name}: Native.fs {sig} != dn_tensor.h {protos[name]}"
+
+
+def test_fsharp_backend_references_only_defined_modules():
+    """B200Backend.fs called B200Transfer / B200Index, which existed nowhere."""
+    src = "".join(open(os.path.join(ROOT, "fsharp", "Tensor.B200", f)).read()
+                  for f in ("Native.fs", "B200Backend.fs", "B200Shard.fs"))
+    src = re.sub(r"//.*", "", src)
+    defined = set(re.findall(r"^module (?:internal |private )?(\w+)", src, flags=re.M))
+    used = set(re.findall(r"\b(B200\w+|Marshalling|Native)\.\w+", src))
+    assert used <= defined, f"undefined F# modules referenced: {sorted(used - defined)}"
+    natives = set(re.findall(r"Native\.(dn_[a-z0-9_]+)", src))
+    assert natives <= set(_fsharp_externs()), sorted(natives - set(_fsharp_externs()))
+
+
+def test_product_package_does_not_import_torch():
+    """north_star: PyTorch is harness plumbing (tests, bench), not part of the product package."""
+    code = ("import sys, deepnet_b200, deepnet_b200.shard, deepnet_b200.fused;"
+            "assert 'torch' not in sys.modules, 'torch imported by the product package'")
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)

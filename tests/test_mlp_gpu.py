@@ -17,7 +17,15 @@ from oracle.host_tensor import HostTensor  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-def test_mlp_step_matches_oracle(cuda_dev):
+@pytest.fixture(params=["fp32", "tf32"])
+def math_mode(request, cuda_dev):
+    """Both precisions of float32 MatMatDot (dn_set_math_mode): the fp32-accurate default and the opt-in tf32 pass."""
+    cuda_dev.SetMathMode(request.param)
+    yield request.param
+    cuda_dev.SetMathMode("fp32")
+
+
+def test_mlp_step_matches_oracle(cuda_dev, math_mode):
     sizes, batch = (784, 192, 160, 10), 256
     rng = np.random.default_rng(51)
     p0 = init_params(rng, sizes)
@@ -40,7 +48,7 @@ def test_mlp_step_matches_oracle(cuda_dev):
         assert np.linalg.norm((cbi - b0) - (hbi - b0)) <= 1e-2 * np.linalg.norm(hbi - b0) + 1e-7
 
 
-def test_mlp_step_full_size_properties(cuda_dev):
+def test_mlp_step_full_size_properties(cuda_dev, math_mode):
     sizes, batch = (784, 4096, 4096, 10), 8192
     rng = np.random.default_rng(52)
     params = [(CudaTensor.ofNumpy(w), CudaTensor.ofNumpy(b)) for w, b in init_params(rng, sizes)]

@@ -13,7 +13,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(240, method="thread")]
 
 
 def _device_count(cuda_dev) -> int:
@@ -23,11 +23,16 @@ def _device_count(cuda_dev) -> int:
     return n.value
 
 
-@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_sharded_ops_single_process(cuda_dev, world):
     import shard_cases
     from deepnet_b200.shard import ShardGroup
     ndev = _device_count(cuda_dev)
+    if world > 4 * ndev:
+        # every rank has a stream that may sit in a wait for a peer's signal; streams beyond the device's hardware
+        # queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default) share a queue, and a kernel queued behind a waiting
+        # stream's wait would never send its signal
+        pytest.skip("more than 4 ranks per device")
     devices = [r % ndev for r in range(world)]
     grp = ShardGroup.single_process(cuda_dev, devices)
     try:

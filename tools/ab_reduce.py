@@ -1,0 +1,67 @@
+"""A/B timing of the C3 reductions with two builds of the library on the SAME box (clocks and power caps differ from
+box to box by a few percent, which is the size of the effects being chased):
+    python tools/ab_reduce.py build/ab/libdeepnet_b200_r01.so deepnet_b200/lib/libdeepnet_b200.so
+Each library runs in its own process, alternating, three rounds; CUDA-event timing of 20 back-to-back calls."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json, statistics
+sys.path.insert(0, os.environ["DN_ROOT"])
+from deepnet_b200 import native
+native.product_library_path = lambda: os.environ["DN_AB_LIB"]
+import ctypes
+_lib = ctypes.CDLL(os.environ["DN_AB_LIB"])
+for table in (native._OPERATOR_SIGNATURES, native._DEVICE_SIGNATURES):   # an older build exports fewer entry points
+    for name in [n for n in table if not hasattr(_lib, "dn_" + n)]:
+        del table[name]
+import torch
+from deepnet_b200 import CudaTensor, Tensor, dtypes
+dev = CudaTensor.dev(); dev.Init(0)
+stream = torch.cuda.current_stream(); dev.SetStream(stream.cuda_stream)
+def w(t, dt): return CudaTensor.usingPtr(t.data_ptr(), tuple(t.shape), dt, owner=t)
+def timed(fn, reps=20):
+    fn(); ts = []
+    for _ in range(7):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        for _ in range(reps): fn()
+        e.record(stream); e.synchronize(); ts.append(s.elapsed_time(e) / reps)
+    return statistics.median(ts)
+out = {}
+tl = torch.rand(262144, 1000, device="cuda") * 100 - 50
+lg = w(tl, dtypes.DN_F32)
+oi, om = Tensor.empty((262144,), dtypes.DN_I64, dev), Tensor.empty((262144,), dtypes.DN_F32, dev)
+nb = 262144 * 1000 * 4
+out["C3 argmax"] = nb / timed(lambda: oi._fill_axis("ArgMaxLastAxis", 1, lg, True)) / 1e6
+out["C3 max"] = nb / timed(lambda: om.FillMaxAxis(1, lg)) / 1e6
+out["C3 sum"] = nb / timed(lambda: om.FillSumAxis(1, lg)) / 1e6
+t2 = torch.rand(16384, 16384, device="cuda") * 100 - 50
+a2 = w(t2, dtypes.DN_F32); o2 = Tensor.empty((16384,), dtypes.DN_F32, dev); o2i = Tensor.empty((16384,), dtypes.DN_I64, dev)
+nb2 = 16384 * 16384 * 4
+out["16384^2 f32 sum1"] = nb2 / timed(lambda: o2.FillSumAxis(1, a2)) / 1e6
+out["16384^2 f32 max1"] = nb2 / timed(lambda: o2.FillMaxAxis(1, a2)) / 1e6
+out["16384^2 f32 argmax1"] = nb2 / timed(lambda: o2i._fill_axis("ArgMaxLastAxis", 1, a2, True)) / 1e6
+out["16384^2 f32 sum0"] = nb2 / timed(lambda: o2.FillSumAxis(0, a2)) / 1e6
+print(json.dumps(out))
+'''
+
+if __name__ == "__main__":
+    libs = [os.path.abspath(p) for p in sys.argv[1:]]
+    res = {p: [] for p in libs}
+    for _ in range(3):
+        for p in libs:
+            env = dict(os.environ, DN_ROOT=ROOT, DN_AB_LIB=p)
+            out = subprocess.run([sys.executable, "-c", WORKER], env=env, capture_output=True, text=True, timeout=300)
+            if out.returncode != 0:
+                print(p, "FAILED", out.stderr[-1500:])
+                continue
+            res[p].append(json.loads(out.stdout.strip().splitlines()[-1]))
+    keys = list(next(iter(res.values()))[0].keys()) if all(res.values()) else []
+    print(f"{'GB/s (median of rounds)':28s}" + "".join(f"{os.path.basename(p)[:26]:>28s}" for p in libs))
+    for k in keys:
+        print(f"{k:28s}" + "".join(f"{sorted(r[k] for r in res[p])[len(res[p]) // 2]:28.1f}" for p in libs))
