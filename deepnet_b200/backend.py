@@ -342,8 +342,9 @@ class TensorCudaDevice(ITensorDevice):
         self.api.call("set_check_errors", 1 if enabled else 0)
 
     def SetMathMode(self, mode: str) -> None:
-        """dn_set_math_mode: "fp32" (default; fp32-accurate MatMatDot, 3xTF32 on the tensor cores) or "tf32"."""
-        self.api.call("set_math_mode", {"fp32": 0, "tf32": 1}[mode])
+        """dn_set_math_mode: "fp32" (default: exact kernel for small products, 3xTF32 on the tensor cores for large
+        ones), "tf32" (one tf32 pass) or "strict" (exact fp32 kernel for every size)."""
+        self.api.call("set_math_mode", {"fp32": 0, "tf32": 1, "strict": 2}[mode])
 
     def LaunchCount(self) -> int:
         return int(self.api.lib.dn_launch_count())

@@ -14,10 +14,11 @@
 // C = A·B with A[M,K] and B[K,N] given as arbitrary strided views: an operand whose K axis is contiguous and
 // TMA-aligned is consumed in place ("K-major"); anything else (an N-contiguous B, a transposed A, odd pitches) is
 // first repacked K-major by the element-wise transpose kernel (dn_copy) into stream-ordered scratch.
-// Precision (dn_set_math_mode): DN_MATH_FP32, the default, delivers fp32 accuracy like the reference's cuBLAS SGEMM —
-// 3xTF32 (hi/lo split of both operands, three MMAs per k-step) for large problems, the exact SIMT kernel for small
-// ones; DN_MATH_TF32 reads the inputs once as TF32 (10-bit mantissa), fp32 accumulation: rel 1e-2 of the fp64
-// oracle per BASELINE.json north_star, at three times the throughput.
+// Precision (dn_set_math_mode): DN_MATH_FP32, the default — the exact SIMT kernel for small problems, 3xTF32 (hi/lo
+// split of both operands, three MMAs per k-step; ~1e-5 relative, limited by the tensor core's truncating
+// accumulator) for large ones; DN_MATH_FP32_STRICT — SIMT for every size; DN_MATH_TF32 reads the inputs once as
+// TF32 (10-bit mantissa), fp32 accumulation: rel 1e-2 of the fp64 oracle per BASELINE.json north_star, at three
+// times the throughput of the default.
 // float64 has no tcgen05 path: a shared-memory tiled SIMT kernel.
 #include <cuda.h>
 
@@ -649,15 +650,20 @@ dn_status gemm_f32_split(float *c, int64_t cm, int64_t cn, const float *a, int64
     return st;
 }
 
-// MatMatDot on float32. DN_MATH_FP32 (default): the result has fp32 accuracy, like the reference's cuBLAS SGEMM
-// (its own test "Single matrix dot" compares with the host at rel 1e-5, Tensor.Test/CudaTests.fs:52-62) — small
-// problems on the exact fp32 SIMT kernel, large ones as 3xTF32 on the tensor cores. DN_MATH_TF32: one tf32 pass.
+// MatMatDot on float32 (dn_set_math_mode).
+//   DN_MATH_FP32 (default): small problems (everything the reference's own tests multiply, e.g. "Single matrix dot",
+//     Tensor.Test/CudaTests.fs:52-62, rel 1e-5 against the host) run on the exact fp32 SIMT kernel; large ones as 3xTF32
+//     on the tensor cores: the INPUT error drops from tf32's 2^-11 to ~2^-21, what remains is the tensor core's
+//     accumulator, which truncates (round toward zero) after every MMA — measured norm-wise 7e-6 at K = 1024
+//     (a single tf32 pass: 5e-4; the SIMT kernel: 1e-7), growing linearly with K.
+//   DN_MATH_FP32_STRICT: the SIMT kernel for every size (IEEE fp32 fused multiply-adds, round to nearest).
+//   DN_MATH_TF32: one tf32 pass (rel 1e-2 per north_star), three times the throughput of the default.
 dn_status gemm_f32(float *c, int64_t cm, int64_t cn, const float *a, int64_t am, int64_t ak, const float *b, int64_t bk,
                    int64_t bn, int64_t M, int64_t N, int64_t K) {
-    if (g_math_mode.load(std::memory_order_relaxed) == DN_MATH_TF32 || M == 0 || N == 0 || K == 0)
-        return gemm_f32_tf32(c, cm, cn, a, am, ak, b, bk, bn, M, N, K);
+    const int mode = g_math_mode.load(std::memory_order_relaxed);
+    if (mode == DN_MATH_TF32 || M == 0 || N == 0 || K == 0) return gemm_f32_tf32(c, cm, cn, a, am, ak, b, bk, bn, M, N, K);
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return set_error(DN_ERR_UNSUPPORTED, "MatMatDot: extent exceeds 2^31-1");
-    if (M * N * K < ((int64_t)1 << 27))
+    if (mode == DN_MATH_FP32_STRICT || M * N * K < ((int64_t)1 << 27))
         return gemm_simt<float>(c, cm, cn, a, am, ak, b, bk, bn, M, N, K, 0, nullptr, nullptr, nullptr, nullptr);
     return gemm_f32_split(c, cm, cn, a, am, ak, b, bk, bn, M, N, K);
 }
@@ -884,7 +890,7 @@ dn_status matvec_t_run(const dn_tensor *t, const dn_tensor *a, const dn_tensor *
 extern "C" {
 
 dn_status dn_set_math_mode(int32_t mode) {
-    if (mode != DN_MATH_FP32 && mode != DN_MATH_TF32) return set_error(DN_ERR_INVALID_ARG, "dn_set_math_mode: bad mode %d", mode);
+    if (mode != DN_MATH_FP32 && mode != DN_MATH_TF32 && mode != DN_MATH_FP32_STRICT) return set_error(DN_ERR_INVALID_ARG, "dn_set_math_mode: bad mode %d", mode);
     g_math_mode.store(mode, std::memory_order_relaxed);
     return DN_OK;
 }

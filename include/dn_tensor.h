@@ -250,11 +250,15 @@ dn_status dn_true_indices(const dn_tensor *t, const dn_tensor *a);
  * ------------------------------------------------------------------------------------------------------------- */
 /* Precision of float32 MatMatDot / BatchedMatMatDot (process-wide). The reference calls cuBLAS SGEMM (full fp32;
  * its test "Single matrix dot", Tensor.Test/CudaTests.fs:52-62, compares with the host at rel 1e-5).
- *   DN_MATH_FP32 (default): fp32-accurate — small problems on an exact fp32 kernel, large ones as 3xTF32 on the
- *                           tensor cores (operands split into two tf32 halves, three tcgen05 MMAs per k-step);
+ *   DN_MATH_FP32 (default): problems below 2^27 multiply-adds (every product the reference's tests form) run on an
+ *                           exact fp32 kernel; larger ones as 3xTF32 on the tensor cores (operands split into two
+ *                           tf32 halves, three tcgen05 MMAs per k-step): input error 2^-21 instead of tf32's 2^-11;
+ *                           the tensor core's accumulator truncates after every MMA, which leaves a norm-wise
+ *                           relative error of ~7e-6 at K = 1024, growing linearly with K;
  *   DN_MATH_TF32          : one tcgen05 pass with tf32 inputs (10-bit mantissa), fp32 accumulation; rel 1e-2 of
- *                           the fp64 result (BASELINE.json north_star), three times the throughput. Opt-in. */
-typedef enum dn_math_mode { DN_MATH_FP32 = 0, DN_MATH_TF32 = 1 } dn_math_mode;
+ *                           the fp64 result (BASELINE.json north_star), three times the throughput. Opt-in;
+ *   DN_MATH_FP32_STRICT   : the exact fp32 kernel (CUDA cores, fused multiply-add, round to nearest) for every size. */
+typedef enum dn_math_mode { DN_MATH_FP32 = 0, DN_MATH_TF32 = 1, DN_MATH_FP32_STRICT = 2 } dn_math_mode;
 dn_status dn_set_math_mode(int32_t mode);
 dn_status dn_get_math_mode(int32_t *mode);
 /* VecVecDot / MatVecDot (TensorBackend.fs:137-138; CudaBackend.fs:383-408). */
