@@ -24,7 +24,7 @@ thread_local PeerSync t_pending = {};
 thread_local bool t_has_pending = false;
 
 constexpr int64_t kFlagBytes = 4096;             // done[8] | counter | counts[2][8]
-constexpr int64_t kCounterOff = 256, kCountsOff = 512;
+constexpr int64_t kCounterOff = 256, kErrorOff = 320, kCountsOff = 512;
 constexpr int64_t kScratchHalf = 8ll << 20;      // partials of reductions over the sharded axis (two halves)
 constexpr int64_t kHeapOff = kFlagBytes + 2 * kScratchHalf;
 
@@ -59,6 +59,7 @@ struct ShardGroup {
     int world = 0;
     int64_t heap_bytes = 0, window_bytes = 0;
     bool connected = false;
+    int nlocal = 0;
     bool grouping = false;  // between dn_shard_group_start and dn_shard_group_end
     ShardRank r[kMaxShardRanks];
 };
@@ -105,6 +106,10 @@ PeerSync make_sync(ShardGroup &g, ShardRank &me, int rank, bool with_data) {
     ps.npeers = n;
     ps.flag_local = reinterpret_cast<uint32_t *>(me.window);
     ps.counter = reinterpret_cast<uint32_t *>(me.window + kCounterOff);
+    ps.error = reinterpret_cast<uint32_t *>(me.window + kErrorOff);
+    // one rank per process: the wait half runs inside the signalling kernel (peer.cuh); several local ranks: as
+    // stream memory operations, deferred to dn_shard_group_end inside a bracket
+    ps.wait_in_kernel = g.nlocal == 1 ? 1 : 0;
     return ps;
 }
 
@@ -115,6 +120,7 @@ __global__ void peer_barrier_kernel(const __grid_constant__ PeerSync ps) {
 // The wait half of the barrier: the stream does not proceed until every rank's flag in the LOCAL window has
 // reached `epoch` (cyclic >=). Stream memory operations: no SM is occupied while waiting.
 dn_status enqueue_wait(const PeerSync &ps) {
+    if (ps.wait_in_kernel) return DN_OK;  // the signalling kernel has already waited
     CUstreamBatchMemOpParams ops[kMaxShardRanks];
     memset(ops, 0, sizeof ops);
     for (int k = 0; k < ps.nflags; ++k) {
@@ -314,6 +320,7 @@ dn_status dn_shard_group_create(int32_t world, int32_t nlocal, const int32_t *lo
     ShardGroup *g = new (std::nothrow) ShardGroup();
     if (!g) return set_error(DN_ERR_OUT_OF_MEMORY, "dn_shard_group_create: out of host memory");
     g->world = world;
+    g->nlocal = nlocal;
     g->heap_bytes = (heap_bytes + 255) / 256 * 256;
     g->window_bytes = kHeapOff + g->heap_bytes;
     int prev = 0;
@@ -458,7 +465,13 @@ dn_status dn_shard_sync(void *group, int32_t rank) {
     dn_status st = get_rank(group, rank, g, me, "dn_shard_sync");
     if (st != DN_OK) return st;
     RankScope scope(*me);
+    uint32_t err = 0;
+    DN_CUDA_TRY(cudaMemcpyAsync(&err, me->window + kErrorOff, sizeof err, cudaMemcpyDeviceToHost, me->stream));
     DN_CUDA_TRY(cudaStreamSynchronize(me->stream));
+    if (err) {
+        cudaMemsetAsync(me->window + kErrorOff, 0, sizeof err, me->stream);
+        return set_error(DN_ERR_CUDA, "shard barrier timed out on rank %d: a rank did not issue the matching collective", rank);
+    }
     return DN_OK;
 }
 

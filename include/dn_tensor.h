@@ -311,7 +311,7 @@ dn_status dn_shard_group_handle(void *group, int32_t rank, void *handle);
 dn_status dn_shard_group_connect(void *group, const void *handles);
 dn_status dn_shard_group_destroy(void *group);
 dn_status dn_shard_set_stream(void *group, int32_t rank, void *stream);
-dn_status dn_shard_sync(void *group, int32_t rank);          /* waits for the rank's stream */
+dn_status dn_shard_sync(void *group, int32_t rank);          /* waits for the rank's stream; reports a barrier that timed out */
 /* Contiguous slab [begin, begin+count) of `nrows` rows owned by `rank`; the remainder goes to the first ranks. */
 dn_status dn_shard_slab(int64_t nrows, int32_t rank, int32_t world, int64_t *begin, int64_t *count);
 /* Symmetric heap: a bump allocator (256-byte granules); reset frees everything. Collective by convention. */

@@ -247,7 +247,7 @@ def test_strict_math_mode_is_exact_fp32(cuda_dev, M, N, K):
         got = (CudaTensor.ofNumpy(a) @ CudaTensor.ofNumpy(b)).toNumpy().astype(np.float64)
     finally:
         cuda_dev.SetMathMode("fp32")
-    assert np.linalg.norm(got - want) <= 1e-6 * np.linalg.norm(want)
+    assert np.linalg.norm(got - want) <= 3e-6 * np.linalg.norm(want)   # sqrt(K) * 2^-24 accumulation, K up to 4096
 
 
 def test_fp32_mode_layouts_and_specials(cuda_dev):

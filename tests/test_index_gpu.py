@@ -192,3 +192,18 @@ def test_compaction_with_32768_position_tiles(cuda_dev):
                           "true_idx or masked"], env=env, capture_output=True, text=True, timeout=900,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+def test_scatter_binned_path_on_the_small_cases():
+    """The bin-then-accumulate Scatter (large dense targets) is forced on for every Scatter case of this file through
+    the DN_SCATTER_BINNED=1 test hook (read once per process, hence the child process); test_configs_gpu.py covers it
+    at the sizes it is meant for."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DN_SCATTER_BINNED") == "1":
+        pytest.skip("already running under the hook")
+    env = dict(os.environ, DN_SCATTER_BINNED="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-k", "scatter", "-q", "-m", "gpu", "-x"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
