@@ -11,6 +11,9 @@
 // unfused call sequence bit for bit.
 #include "ew_ops.cuh"
 
+#include <cstdlib>
+#include <string>
+
 using namespace dn;
 
 namespace {
@@ -201,6 +204,115 @@ struct FusedF : FusedSig<T, NS>::type {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Precompiled programs. The interpreter above is issue-bound (43 thread-instructions per element, 63-81 % of the HBM
+// rate — profiles/r01d_fused_tanh_grad); the expressions that actually occur (the C1 benchmark expression, every
+// element-wise chain of the MLP training step) are ALSO compiled as ordinary element-wise functors — expression
+// templates over the same UnaryF / BinaryF functors, in this -fmad=false translation unit, so each node rounds exactly
+// like the operator it stands for and the result is the same bits — and run through the same planner and the same
+// 256-bit vector / register-transpose kernels as any single operator. A program is recognised by the canonical
+// string of its expression tree (registers renamed away, constants by position); anything else is interpreted.
+// ---------------------------------------------------------------------------------------------------------------
+template <int K> struct XS {  // source K
+    template <class T> __device__ __forceinline__ static T ev(const T (&s)[3], const T *) { return s[K]; }
+};
+template <int I> struct XC {  // I-th constant of the program
+    template <class T> __device__ __forceinline__ static T ev(const T (&)[3], const T *c) { return c[I]; }
+};
+template <int OP, class A> struct XU {
+    template <class T> __device__ __forceinline__ static T ev(const T (&s)[3], const T *c) {
+        return UnaryF<T, OP>()(A::template ev<T>(s, c));
+    }
+};
+template <int OP, class A, class B> struct XB {
+    template <class T> __device__ __forceinline__ static T ev(const T (&s)[3], const T *c) {
+        return BinaryF<T, OP>()(A::template ev<T>(s, c), B::template ev<T>(s, c));
+    }
+};
+
+template <class T, int NS, class E>
+struct SpecF : FusedSig<T, NS>::type {
+    T c[4];
+    __device__ __forceinline__ T operator()(T a) const { const T s[3] = {a, a, a}; return E::template ev<T>(s, c); }
+    __device__ __forceinline__ T operator()(T a, T b) const { const T s[3] = {a, b, b}; return E::template ev<T>(s, c); }
+    __device__ __forceinline__ T operator()(T a, T b, T d) const { const T s[3] = {a, b, d}; return E::template ev<T>(s, c); }
+};
+
+template <class T, int NS, class E>
+dn_status run_spec(EwPlan &plan, const double *consts, int nconst) {
+    SpecF<T, NS, E> f;
+    for (int i = 0; i < 4; ++i) f.c[i] = i < nconst ? (T)consts[i] : T(0);
+    return ew_run(plan, f);
+}
+
+// Canonical form: u<op>(x), b<op>(x,y), s<k>, k<i> (i = position of the CONST instruction among the CONSTs).
+std::string canonical(const dn_fused_instr *prog, int n, int nsrc, double *consts, int *nconst) {
+    std::string reg[DN_FUSED_REGS];
+    for (int k = 0; k < nsrc; ++k) reg[k] = "s" + std::to_string(k);
+    *nconst = 0;
+    std::string last;
+    for (int k = 0; k < n; ++k) {
+        const dn_fused_instr &in = prog[k];
+        std::string v;
+        if (in.kind == DN_FUSED_CONST) {
+            v = "k" + std::to_string(*nconst);
+            if (*nconst < 4) consts[*nconst] = in.imm;
+            ++*nconst;
+        } else if (in.kind == DN_FUSED_UNARY) {
+            v = "u" + std::to_string(in.op) + "(" + reg[in.a] + ")";
+        } else {
+            v = "b" + std::to_string(in.op) + "(" + reg[in.a] + "," + reg[in.b] + ")";
+        }
+        if (v.size() > 256) return std::string();  // nothing that long is precompiled
+        reg[in.dst] = v;
+        last = v;
+    }
+    return last;
+}
+
+using S0 = XS<0>;
+using S1 = XS<1>;
+using S2 = XS<2>;
+using K0 = XC<0>;
+// a*b + sin(a)                      (C1, Tensor.Benchmark-shaped)
+using E_c1 = XB<DN_ADD, XB<DN_MULTIPLY, S0, S1>, XU<DN_SIN, S0>>;
+// (z + b).tanh()                    (MLP hidden layer: bias + activation)
+using E_bias_tanh = XU<DN_TANH, XB<DN_ADD, S0, S1>>;
+// (z - c).exp()                     (softmax numerator)
+using E_sub_exp = XU<DN_EXP, XB<DN_SUBTRACT, S0, S1>>;
+// -(t * log p)                      (cross-entropy terms)
+using E_xent = XU<DN_UNARY_MINUS, XB<DN_MULTIPLY, S0, XU<DN_LOG, S1>>>;
+// (p - t) / k                       (softmax + cross-entropy gradient)
+using E_diff_div = XB<DN_DIVIDE, XB<DN_SUBTRACT, S0, S1>, K0>;
+// d * (k - h*h)                     (tanh gradient)
+using E_tanh_grad = XB<DN_MULTIPLY, S0, XB<DN_SUBTRACT, K0, XB<DN_MULTIPLY, S1, S1>>>;
+// w - g*k                           (SGD update)
+using E_sgd = XB<DN_SUBTRACT, S0, XB<DN_MULTIPLY, S1, K0>>;
+// (a - b) * c / (|c| + k)           (three-source example of the sweep)
+using E_three = XB<DN_DIVIDE, XB<DN_MULTIPLY, XB<DN_SUBTRACT, S0, S1>, S2>, XB<DN_ADD, XU<DN_ABS, S2>, K0>>;
+
+template <class T>
+bool run_precompiled(const std::string &key, int nsrc, EwPlan &plan, const double *consts, int nconst, dn_status *st) {
+    auto u = [](int op, const std::string &x) { return "u" + std::to_string(op) + "(" + x + ")"; };
+    auto b = [](int op, const std::string &x, const std::string &y) { return "b" + std::to_string(op) + "(" + x + "," + y + ")"; };
+    const std::string s0 = "s0", s1 = "s1", s2 = "s2", k0 = "k0";
+    if (nsrc == 2) {
+        if (key == b(DN_ADD, b(DN_MULTIPLY, s0, s1), u(DN_SIN, s0))) { *st = run_spec<T, 2, E_c1>(plan, consts, nconst); return true; }
+        if (key == u(DN_TANH, b(DN_ADD, s0, s1))) { *st = run_spec<T, 2, E_bias_tanh>(plan, consts, nconst); return true; }
+        if (key == u(DN_EXP, b(DN_SUBTRACT, s0, s1))) { *st = run_spec<T, 2, E_sub_exp>(plan, consts, nconst); return true; }
+        if (key == u(DN_UNARY_MINUS, b(DN_MULTIPLY, s0, u(DN_LOG, s1)))) { *st = run_spec<T, 2, E_xent>(plan, consts, nconst); return true; }
+        if (key == b(DN_DIVIDE, b(DN_SUBTRACT, s0, s1), k0)) { *st = run_spec<T, 2, E_diff_div>(plan, consts, nconst); return true; }
+        if (key == b(DN_MULTIPLY, s0, b(DN_SUBTRACT, k0, b(DN_MULTIPLY, s1, s1)))) { *st = run_spec<T, 2, E_tanh_grad>(plan, consts, nconst); return true; }
+        if (key == b(DN_SUBTRACT, s0, b(DN_MULTIPLY, s1, k0))) { *st = run_spec<T, 2, E_sgd>(plan, consts, nconst); return true; }
+    } else if (nsrc == 3) {
+        if (key == b(DN_DIVIDE, b(DN_MULTIPLY, b(DN_SUBTRACT, s0, s1), s2), b(DN_ADD, u(DN_ABS, s2), k0))) {
+            *st = run_spec<T, 3, E_three>(plan, consts, nconst);
+            return true;
+        }
+    }
+    return false;
+}
+
 template <class T, int NS>
 dn_status run_fused(EwPlan &plan, const dn_fused_instr *prog, int n) {
     FusedF<T, NS> f;
@@ -250,6 +362,18 @@ extern "C" dn_status dn_fused_elemwise(const dn_tensor *t, const dn_tensor *cons
     EwPlan plan;
     dn_status st = ew_make_plan(plan, t, srcs, nsrc);
     if (st != DN_OK) return st;
+    // a precompiled program? (DN_FUSED_INTERPRET=1, a test hook, forces the interpreter so that both stay covered)
+    static const bool interpret_only = [] { const char *e = getenv("DN_FUSED_INTERPRET"); return e && e[0] == '1'; }();
+    if (!interpret_only) {
+        double consts[4];
+        int nconst = 0;
+        const std::string key = canonical(prog, ninstr, nsrc, consts, &nconst);
+        if (!key.empty() && nconst <= 4) {
+            const bool hit = t->dtype == DN_F32 ? run_precompiled<float>(key, nsrc, plan, consts, nconst, &st)
+                                                : run_precompiled<double>(key, nsrc, plan, consts, nconst, &st);
+            if (hit) return st;
+        }
+    }
     if (t->dtype == DN_F32) {
         if (nsrc == 1) return run_fused<float, 1>(plan, prog, ninstr);
         if (nsrc == 2) return run_fused<float, 2>(plan, prog, ninstr);

@@ -100,3 +100,19 @@ def test_fused_program_validation(cuda_dev):
     with pytest.raises(ValueError):   # more live values than registers
         Tensor.fused(lambda x: ((((x + 1.0) * (x + 2.0)) * ((x + 3.0) * (x + 4.0))) * (((x + 5.0) * (x + 6.0)) * ((x + 7.0) * (x + 8.0)))) *
                      ((((x + 9.0) * (x + 10.0)) * ((x + 11.0) * (x + 12.0))) * (((x + 13.0) * (x + 14.0)) * ((x + 15.0) * (x + 16.0)))), a)
+
+
+def test_interpreter_stays_covered():
+    """Programs that have a precompiled form (a*b + sin a, the MLP's element-wise chains) no longer reach the
+    interpreter; the DN_FUSED_INTERPRET=1 test hook (read once per process, hence the child process) sends everything
+    through it again, so both evaluators are held to the same bit-identity checks of this file and of the MLP step."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DN_FUSED_INTERPRET") == "1":
+        pytest.skip("already running under the hook")
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, DN_FUSED_INTERPRET="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), os.path.join(here, "test_mlp_gpu.py"),
+                          "-k", "fused", "-q", "-m", "gpu", "-x"], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
