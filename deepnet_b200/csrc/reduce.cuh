@@ -235,6 +235,11 @@ struct ArgOp {
     struct State { T val; int64_t idx; };
     static constexpr bool ordered = false;
     __device__ static bool better(T a, T b) { return IsMax ? a > b : a < b; }
+    // extremum of two candidates, NaNs ignored (a NaN never wins an arg fold): one FMNMX / IMNMX
+    __device__ static T pick(T a, T b) {
+        if constexpr (kIsFloat<T>) return IsMax ? fmax(a, b) : fmin(a, b);
+        else return IsMax ? (a > b ? a : b) : (a < b ? a : b);
+    }
     __device__ static State identity() {
         return State{IsMax ? Limits<T>::lowest() : Limits<T>::max(), (int64_t)DN_NOT_FOUND};
     }
@@ -368,12 +373,22 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
                 if (j < n) probe += v[j];
             if constexpr (IsFusedArgOp<Op>::value) {  // the arg fold: NaNs never win (strict compare)
                 const int r0 = (int)(i0 - begin);
+                // a new extremum is rare (O(log n) times per lane): test the vector's extremum first, search only then
+                bool look = true;
+                if (n == VEC) {
+                    T m = v[0];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j)
-                    if (j < n && Op::better(v[j], st.aval)) {
-                        st.aval = v[j];
-                        ridx = r0 + j;
-                    }
+                    for (int j = 1; j < VEC; ++j) m = Op::A::pick(m, v[j]);
+                    look = Op::better(m, st.aval);
+                }
+                if (look) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                        if (j < n && Op::better(v[j], st.aval)) {
+                            st.aval = v[j];
+                            ridx = r0 + j;
+                        }
+                }
             }
             if (__any_sync(kFull, probe != probe)) {  // rare
                 int64_t my_nan = -1;
@@ -401,12 +416,22 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
             // (value, index) pairs: the lane tracks a 32-bit index relative to `begin` (one select instead of a
             // 64-bit pair per element); it is widened once at the end of the part
             const int r0 = (int)(i0 - begin);
+            // a new extremum is rare (O(log n) times per lane): test the vector's extremum first, search only then
+            bool look = true;
+            if (n == VEC) {
+                T m = v[0];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j)
-                if (j < n && Op::better(v[j], st.val)) {
-                    st.val = v[j];
-                    ridx = r0 + j;
-                }
+                for (int j = 1; j < VEC; ++j) m = Op::pick(m, v[j]);
+                look = Op::better(m, st.val);
+            }
+            if (look) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    if (j < n && Op::better(v[j], st.val)) {
+                        st.val = v[j];
+                        ridx = r0 + j;
+                    }
+            }
         } else {
             if constexpr (HasPacked16<Op>::value) {
                 if (n == VEC) {  // v is a 16-byte aligned Pack
