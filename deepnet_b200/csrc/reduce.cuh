@@ -373,22 +373,12 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
                 if (j < n) probe += v[j];
             if constexpr (IsFusedArgOp<Op>::value) {  // the arg fold: NaNs never win (strict compare)
                 const int r0 = (int)(i0 - begin);
-                // a new extremum is rare (O(log n) times per lane): test the vector's extremum first, search only then
-                bool look = true;
-                if (n == VEC) {
-                    T m = v[0];
 #pragma unroll
-                    for (int j = 1; j < VEC; ++j) m = Op::A::pick(m, v[j]);
-                    look = Op::better(m, st.aval);
-                }
-                if (look) {
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j)
-                        if (j < n && Op::better(v[j], st.aval)) {
-                            st.aval = v[j];
-                            ridx = r0 + j;
-                        }
-                }
+                for (int j = 0; j < VEC; ++j)
+                    if (j < n && Op::better(v[j], st.aval)) {
+                        st.aval = v[j];
+                        ridx = r0 + j;
+                    }
             }
             if (__any_sync(kFull, probe != probe)) {  // rare
                 int64_t my_nan = -1;
@@ -415,23 +405,15 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
         } else if constexpr (IsArgOp<Op>::value) {
             // (value, index) pairs: the lane tracks a 32-bit index relative to `begin` (one select instead of a
             // 64-bit pair per element); it is widened once at the end of the part
+            // (testing the vector's extremum first and searching only on a hit was tried: the branch costs more than the
+            // selects it saves — C3 ArgMax 6.42 -> 5.98 TB/s)
             const int r0 = (int)(i0 - begin);
-            // a new extremum is rare (O(log n) times per lane): test the vector's extremum first, search only then
-            bool look = true;
-            if (n == VEC) {
-                T m = v[0];
 #pragma unroll
-                for (int j = 1; j < VEC; ++j) m = Op::pick(m, v[j]);
-                look = Op::better(m, st.val);
-            }
-            if (look) {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j)
-                    if (j < n && Op::better(v[j], st.val)) {
-                        st.val = v[j];
-                        ridx = r0 + j;
-                    }
-            }
+            for (int j = 0; j < VEC; ++j)
+                if (j < n && Op::better(v[j], st.val)) {
+                    st.val = v[j];
+                    ridx = r0 + j;
+                }
         } else {
             if constexpr (HasPacked16<Op>::value) {
                 if (n == VEC) {  // v is a 16-byte aligned Pack
