@@ -204,19 +204,19 @@ __global__ void __launch_bounds__(kIdxThreads) scatter_kernel(const __grid_const
     } while (0)
 
 // ---------------------------------------------------------------------------------------------------------------
-// Scatter into a LARGE dense target: bin, then accumulate in shared memory.
+// Scatter into a LARGE dense target: partition by target bin, then accumulate in shared memory.
 //
 // One global atomic per element is bound by the L2 atomic units (2^26 random int64 adds: 2.9 ms, 14 % of the HBM
-// rate, DRAM a third busy — profiles/r01_scatter). Instead the (target index, value) pairs are first PARTITIONED by
+// rate — 2.5 ms even into a target that lives in L2). Instead the (target index, value) pairs are PARTITIONED by
 // target bin (a bin = the 64 KiB of the target one CTA can hold in shared memory), then every bin is summed with
-// shared-memory atomics and written out once, coalesced — which is also the zero-fill (CudaBackend.fs:379):
-//   hist       per-CTA histogram of the bins its chunk of the source hits            (reads the indices)
-//   offsets    scan over (bin, CTA): where each CTA's run of each bin starts         (tiny)
-//   partition  every CTA re-walks its chunk and drops (index-in-bin u16, value) at its shared-memory cursors
-//   accumulate one CTA per bin: zero 64 KiB of shared memory, add the bin's pairs, store the bin
-// DRAM traffic: 8kN + (8k+s)N + (2+s)N written, (2+s)N read again, sT written — about 1.3x the algorithmic bytes, all
-// of it streaming. Integer sums are exact in any order; floating-point sums are order-dependent exactly as with
-// global atomics.
+// shared-memory atomics and written out once, coalesced — which is also the zero-fill (CudaBackend.fs:379).
+// The partition runs in TWO levels (<= 64 coarse bins, then <= 128 fine bins inside each): every CTA then has at
+// most ~128 output runs of thousands of elements open, which L2 merges into whole lines. (A single 8192-way pass
+// keeps CTAs x bins = 2.4 M runs of ~27 elements open, far more lines than L2 holds: measured 5.6 ms.)
+//   level 1   hist (reads the indices) -> offsets -> partition: (index u32, value) pairs grouped by coarse bin
+//   level 2   hist (reads the u32 indices) -> offsets -> partition: (index-in-bin u16, value) grouped by fine bin
+//   accumulate: one CTA per fine bin: zero 64 KiB of shared memory, add the bin's pairs, store the bin
+// Integer sums are exact in any order; floating-point sums are order-dependent exactly as with global atomics.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kBinThreads = 512;
 constexpr int kBinSmemBytes = 64 * 1024;
@@ -224,13 +224,17 @@ constexpr int kMaxBins = 8192;
 
 struct BinParams {
     GSParams gs;
-    uint32_t nbins, bin_log, chunk;   // elements per bin = 1 << bin_log; source positions per CTA
+    uint32_t n;                       // elements
+    uint32_t nbins, bin_log, chunk;   // bin of an element = lin >> bin_log; positions per CTA
     uint32_t elem_log;                // log2(sizeof accumulator element)
     uint64_t nt;                      // target elements
-    uint32_t *cta_hist;               // [gridDim.x][nbins]: counts, then (after offsets) absolute start positions
+    uint32_t *cta_hist;               // [gridDim.x][nbins]: counts, then (after offsets) start positions inside the bin
     uint32_t *bin_start;              // [nbins + 1]
-    uint16_t *lows;                   // [n]
-    char *vals;                       // [n] accumulator elements
+    const uint32_t *in_lin;           // level 2 input: pairs grouped by coarse bin
+    const char *in_vals;
+    uint32_t *out_lin;                // level 1 output
+    uint16_t *out_low;                // level 2 output: index inside the fine bin
+    char *out_vals;
 };
 
 // Linear target element index of walked position f, or false when an index is out of range.
@@ -242,28 +246,39 @@ __device__ __forceinline__ bool bin_target(const BinParams &p, uint32_t f, int64
     return ok;
 }
 
-template <int NDI, int NDO>
+// PAIRS = false: level 1, positions are walked through the index tensors; PAIRS = true: level 2, positions are pairs.
+template <bool PAIRS, int NDI, int NDO>
 __global__ void __launch_bounds__(kBinThreads) scatter_hist_kernel(const __grid_constant__ BinParams p) {
     extern __shared__ uint32_t sh_hist[];
     for (uint32_t b = threadIdx.x; b < p.nbins; b += kBinThreads) sh_hist[b] = 0;
     __syncthreads();
     const uint64_t begin = (uint64_t)blockIdx.x * p.chunk;
     uint64_t end = begin + p.chunk;
-    if (end > p.gs.n) end = p.gs.n;
-    constexpr int U = 4;  // index loads of four positions in flight per thread
+    if (end > p.n) end = p.n;
+    constexpr int U = 4;  // loads of four positions in flight per thread
     for (uint64_t base = begin; base < end; base += (uint64_t)kBinThreads * U) {
         uint32_t lin[U];
         int state[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const uint64_t f = base + (uint32_t)j * kBinThreads + threadIdx.x;
-            int64_t so;
-            state[j] = f < end ? (bin_target<NDI, NDO>(p, (uint32_t)f, so, lin[j]) ? 1 : 2) : 0;
+            state[j] = 0;
+            if (f < end) {
+                if constexpr (PAIRS) {
+                    lin[j] = p.in_lin[f];
+                    state[j] = 1;
+                } else {
+                    int64_t so;
+                    state[j] = bin_target<NDI, NDO>(p, (uint32_t)f, so, lin[j]) ? 1 : 2;
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            if (state[j] == 1) atomicAdd(&sh_hist[lin[j] >> p.bin_log], 1u);
-            else if (state[j] == 2) atomicExch(p.gs.err, 1);
+            // an element with an out-of-range index raises the error flag and travels on as "add 0 to element 0",
+            // so that both levels see the same number of elements
+            if (state[j] == 2) { atomicExch(p.gs.err, 1); lin[j] = 0; }
+            if (state[j] != 0) atomicAdd(&sh_hist[lin[j] >> p.bin_log], 1u);
         }
     }
     __syncthreads();
@@ -313,7 +328,7 @@ __global__ void __launch_bounds__(1024) scatter_scan_kernel(uint32_t *bin_start,
     if (threadIdx.x == 1023) bin_start[nbins] = part[1023];
 }
 
-template <class TS, class TA, int NDI, int NDO>
+template <bool PAIRS, class TS, class TA, int NDI, int NDO>
 __global__ void __launch_bounds__(kBinThreads) scatter_partition_kernel(const __grid_constant__ BinParams p) {
     extern __shared__ uint32_t sh_cur[];
     const uint32_t *mine = p.cta_hist + (uint64_t)blockIdx.x * p.nbins;
@@ -321,36 +336,59 @@ __global__ void __launch_bounds__(kBinThreads) scatter_partition_kernel(const __
     __syncthreads();
     const uint64_t begin = (uint64_t)blockIdx.x * p.chunk;
     uint64_t end = begin + p.chunk;
-    if (end > p.gs.n) end = p.gs.n;
+    if (end > p.n) end = p.n;
     constexpr int U = 4;
     const uint32_t mask = (1u << p.bin_log) - 1;
-    TA *vals = reinterpret_cast<TA *>(p.vals);
+    TA *vals = reinterpret_cast<TA *>(p.out_vals);
+    const TA *in_vals = reinterpret_cast<const TA *>(p.in_vals);
     for (uint64_t base = begin; base < end; base += (uint64_t)kBinThreads * U) {
         uint32_t lin[U];
         int64_t so[U];
-        bool ok[U];
+        bool ok[U], valid[U];
         TA v[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const uint64_t f = base + (uint32_t)j * kBinThreads + threadIdx.x;
-            ok[j] = f < end && bin_target<NDI, NDO>(p, (uint32_t)f, so[j], lin[j]);
+            valid[j] = true;
+            if constexpr (PAIRS) {
+                ok[j] = f < end;
+                if (ok[j]) { lin[j] = p.in_lin[f]; v[j] = in_vals[f]; }
+            } else {
+                ok[j] = f < end;
+                valid[j] = ok[j] && bin_target<NDI, NDO>(p, (uint32_t)f, so[j], lin[j]);
+                if (!valid[j]) lin[j] = 0;
+            }
         }
+        if constexpr (!PAIRS) {
 #pragma unroll
-        for (int j = 0; j < U; ++j)
-            if (ok[j]) v[j] = (TA)*reinterpret_cast<const TS *>(p.gs.it_ptr + so[j]);
+            for (int j = 0; j < U; ++j)
+                if (ok[j]) v[j] = valid[j] ? (TA)*reinterpret_cast<const TS *>(p.gs.it_ptr + so[j]) : TA(0);
+        }
 #pragma unroll
         for (int j = 0; j < U; ++j)
             if (ok[j]) {
                 const uint32_t pos = atomicAdd(&sh_cur[lin[j] >> p.bin_log], 1u);
-                p.lows[pos] = (uint16_t)(lin[j] & mask);
+                if constexpr (PAIRS) p.out_low[pos] = (uint16_t)(lin[j] & mask);
+                else p.out_lin[pos] = lin[j];
                 vals[pos] = v[j];
             }
     }
 }
 
+// Shared-memory add. 64-bit integers: two 32-bit adds, the carry of the low word (known from the value the low add
+// returns) rides on the high add — additions commute, so the final words are right whatever the interleaving; the
+// native 64-bit form compiles to a compare-and-swap loop (ATOMS.CAST.SPIN.64).
 template <class T> __device__ __forceinline__ void smem_add(T *addr, T v) {
-    if constexpr (sizeof(T) == 8 && std::is_integral<T>::value) atomicAdd(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)v);
-    else atomicAdd(addr, v);
+    if constexpr (sizeof(T) == 8 && std::is_integral<T>::value) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(addr);
+        const uint64_t u = (uint64_t)v;
+        const uint32_t lo = (uint32_t)u, hi = (uint32_t)(u >> 32);
+        const uint32_t old = atomicAdd(w, lo);
+        const uint32_t carry = (uint32_t)(old + lo < old);
+        if (hi + carry != 0 || (hi == 0xffffffffu && carry)) atomicAdd(w + 1, hi + carry);
+    } else {
+        atomicAdd(addr, v);
+    }
 }
 
 template <class TA>
@@ -358,7 +396,7 @@ __global__ void __launch_bounds__(kBinThreads) scatter_accumulate_kernel(const _
     extern __shared__ __align__(16) unsigned char sh_raw[];
     TA *acc = reinterpret_cast<TA *>(sh_raw);
     const uint32_t bin_elems = 1u << p.bin_log;
-    const TA *vals = reinterpret_cast<const TA *>(p.vals);
+    const TA *vals = reinterpret_cast<const TA *>(p.out_vals);
     TA *target = reinterpret_cast<TA *>(p.gs.other_ptr);
     for (uint32_t b = blockIdx.x; b < p.nbins; b += gridDim.x) {
         for (uint32_t i = threadIdx.x; i < bin_elems; i += kBinThreads) acc[i] = TA(0);
@@ -371,7 +409,7 @@ __global__ void __launch_bounds__(kBinThreads) scatter_accumulate_kernel(const _
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const uint32_t i = base + j * kBinThreads + threadIdx.x;
-                if (i < hi) { l[j] = p.lows[i]; v[j] = vals[i]; }
+                if (i < hi) { l[j] = p.out_low[i]; v[j] = vals[i]; }
             }
 #pragma unroll
             for (int j = 0; j < U; ++j) {
@@ -397,24 +435,38 @@ bool dense_row_major(const dn_tensor *t) {
     return true;
 }
 
+// hist -> offsets -> scan -> partition for one level. `p` carries the level's bins, inputs and outputs.
+template <bool PAIRS, class TS, class TA>
+dn_status scatter_partition_level(BinParams &p, int grid) {
+    const size_t hist_smem = (size_t)p.nbins * 4;
+    DN_GS_RANK_DISPATCH(p.gs.nd_it, p.gs.nd_other,
+                        DN_LAUNCH((scatter_hist_kernel<PAIRS, NDI, NDO>), grid, kBinThreads, hist_smem, p));
+    DN_LAUNCH(scatter_offsets_kernel, (unsigned)((p.nbins + 255) / 256), 256, 0, p.cta_hist, p.bin_start, p.nbins, (uint32_t)grid);
+    DN_LAUNCH(scatter_scan_kernel, 1, 1024, 0, p.bin_start, p.nbins);
+    DN_GS_RANK_DISPATCH(p.gs.nd_it, p.gs.nd_other,
+                        DN_LAUNCH((scatter_partition_kernel<PAIRS, TS, TA, NDI, NDO>), grid, kBinThreads, hist_smem, p));
+    return launch_status("scatter partition kernels");
+}
+
 // Returns DN_OK with *done = false when the problem does not qualify (the caller runs the atomic kernel).
 template <class TS, class TA>
 dn_status scatter_binned(const GSParams &gs, const dn_tensor *acc, int64_t nt, bool *done) {
     *done = false;
     const int esz = (int)sizeof(TA);
-    const uint32_t bin_log = esz == 8 ? 13 : 14;   // 64 KiB of accumulators per CTA
-    const int64_t nbins = (nt + (1ll << bin_log) - 1) >> bin_log;
-    // NOT the default yet: measured on B200 (tools/scatter_probe.py, 2^26 random int64 adds into 2^26 cells) this
-    // path takes 5.6 ms against 2.9 ms for one warp-aggregated L2 atomic per element — the single-pass partition
-    // keeps CTAs x bins = 2.4 M write runs open at once (far more lines than L2 holds, so most pairs reach DRAM as
-    // partial-sector read-modify-writes) and 64-bit shared-memory adds compile to a CAS loop (ATOMS.CAST.SPIN.64).
-    // DN_SCATTER_BINNED=1 turns it on (at any size) for the parity tests and for further work.
-    static const bool enabled = [] { const char *e = getenv("DN_SCATTER_BINNED"); return e && e[0] == '1'; }();
-    if (!enabled || nbins > kMaxBins || !dense_row_major(acc) || gs.n == 0 || nt == 0) return DN_OK;
+    const uint32_t fine_log = esz == 8 ? 13 : 14;   // 64 KiB of accumulators per CTA
+    const int64_t nfine = (nt + (1ll << fine_log) - 1) >> fine_log;
+    // DN_SCATTER_BINNED: 0 = never, 1 = always (parity tests at small sizes); default: large problems only
+    static const int mode = [] { const char *e = getenv("DN_SCATTER_BINNED"); return e ? atoi(e) : -1; }();
+    if (mode == 0 || nfine > kMaxBins || !dense_row_major(acc) || gs.n == 0 || nt == 0) return DN_OK;
+    if (mode != 1 && (gs.n < (1u << 22) || nt < (1ll << 20))) return DN_OK;
+    // coarse bins: at most 64, each a whole number of fine bins (at most 128 of them)
+    uint32_t coarse_log = fine_log;
+    while (((nt + (1ll << coarse_log) - 1) >> coarse_log) > 64) ++coarse_log;
+    const int64_t ncoarse = (nt + (1ll << coarse_log) - 1) >> coarse_log;
+    const bool two_level = coarse_log > fine_log;
     BinParams p;
     p.gs = gs;
-    p.nbins = (uint32_t)nbins;
-    p.bin_log = bin_log;
+    p.n = gs.n;
     p.elem_log = esz == 8 ? 3 : 2;
     p.nt = (uint64_t)nt;
     const int nctas = sm_count() * 2;
@@ -422,17 +474,20 @@ dn_status scatter_binned(const GSParams &gs, const dn_tensor *acc, int64_t nt, b
     chunk = (chunk + kBinThreads * 4 - 1) / (kBinThreads * 4) * (kBinThreads * 4);
     p.chunk = chunk;
     const int grid = (int)(((uint64_t)gs.n + chunk - 1) / chunk);
-    void *s_hist = nullptr, *s_start = nullptr, *s_lows = nullptr, *s_vals = nullptr;
-    dn_status st = scratch_alloc((size_t)grid * nbins * 4, &s_hist);
-    if (st == DN_OK) st = scratch_alloc((size_t)(nbins + 1) * 4, &s_start);
-    if (st == DN_OK) st = scratch_alloc((size_t)gs.n * 2, &s_lows);
-    if (st == DN_OK) st = scratch_alloc((size_t)gs.n * esz, &s_vals);
+    void *s_hist = nullptr, *s_start = nullptr, *s_lin = nullptr, *s_vals1 = nullptr, *s_low = nullptr, *s_vals2 = nullptr;
+    dn_status st = scratch_alloc((size_t)grid * nfine * 4, &s_hist);
+    if (st == DN_OK) st = scratch_alloc((size_t)(nfine + 1) * 4, &s_start);
+    if (st == DN_OK && two_level) st = scratch_alloc((size_t)gs.n * 4, &s_lin);
+    if (st == DN_OK && two_level) st = scratch_alloc((size_t)gs.n * esz, &s_vals1);
+    if (st == DN_OK) st = scratch_alloc((size_t)gs.n * 2, &s_low);
+    if (st == DN_OK) st = scratch_alloc((size_t)gs.n * esz, &s_vals2);
     if (st == DN_OK) {
         p.cta_hist = static_cast<uint32_t *>(s_hist);
         p.bin_start = static_cast<uint32_t *>(s_start);
-        p.lows = static_cast<uint16_t *>(s_lows);
-        p.vals = static_cast<char *>(s_vals);
-        const size_t hist_smem = (size_t)nbins * 4;
+        p.in_lin = nullptr;
+        p.in_vals = nullptr;
+        p.out_lin = static_cast<uint32_t *>(s_lin);
+        p.out_low = static_cast<uint16_t *>(s_low);
         static std::atomic<bool> configured[64];
         int dev = 0;
         cudaGetDevice(&dev);
@@ -440,20 +495,33 @@ dn_status scatter_binned(const GSParams &gs, const dn_tensor *acc, int64_t nt, b
             cudaFuncSetAttribute(scatter_accumulate_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBinSmemBytes);
             if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
         }
-        DN_GS_RANK_DISPATCH(gs.nd_it, gs.nd_other, DN_LAUNCH((scatter_hist_kernel<NDI, NDO>), grid, kBinThreads, hist_smem, p));
-        DN_LAUNCH(scatter_offsets_kernel, (unsigned)((nbins + 255) / 256), 256, 0, p.cta_hist, p.bin_start, p.nbins, (uint32_t)grid);
-        DN_LAUNCH(scatter_scan_kernel, 1, 1024, 0, p.bin_start, p.nbins);
-        DN_GS_RANK_DISPATCH(gs.nd_it, gs.nd_other,
-                            DN_LAUNCH((scatter_partition_kernel<TS, TA, NDI, NDO>), grid, kBinThreads, hist_smem, p));
-        const int acc_grid = nbins < (int64_t)sm_count() * 3 ? (int)nbins : sm_count() * 3;
-        DN_LAUNCH((scatter_accumulate_kernel<TA>), acc_grid, kBinThreads, kBinSmemBytes, p);
-        st = launch_status("binned scatter kernels");
+        if (two_level) {
+            p.nbins = (uint32_t)ncoarse;
+            p.bin_log = coarse_log;
+            p.out_vals = static_cast<char *>(s_vals1);
+            st = scatter_partition_level<false, TS, TA>(p, grid);
+            p.in_lin = p.out_lin;
+            p.in_vals = p.out_vals;
+        }
+        if (st == DN_OK) {
+            p.nbins = (uint32_t)nfine;
+            p.bin_log = fine_log;
+            p.out_vals = static_cast<char *>(s_vals2);
+            st = two_level ? scatter_partition_level<true, TS, TA>(p, grid) : scatter_partition_level<false, TS, TA>(p, grid);
+        }
+        if (st == DN_OK) {
+            const int acc_grid = nfine < (int64_t)sm_count() * 3 ? (int)nfine : sm_count() * 3;
+            DN_LAUNCH((scatter_accumulate_kernel<TA>), acc_grid, kBinThreads, kBinSmemBytes, p);
+            st = launch_status("scatter accumulate kernel");
+        }
         *done = st == DN_OK;
     }
     scratch_free(s_hist);
     scratch_free(s_start);
-    scratch_free(s_lows);
-    scratch_free(s_vals);
+    scratch_free(s_lin);
+    scratch_free(s_vals1);
+    scratch_free(s_low);
+    scratch_free(s_vals2);
     return st;
 }
 

@@ -4,7 +4,7 @@
 // A sharded launch stores every output element into the local result buffer AND into the same offset of every
 // peer's copy of it (plain stores to peer-mapped memory: NVLink / NVSwitch P2P, or CUDA-IPC mappings between
 // processes). The last CTA of the grid to finish then publishes this rank's epoch into every rank's flag array
-// (system-scope release stores). The WAIT half of the barrier comes in two forms (shard.cu picks):
+// (one system-scope fence, then relaxed system-scope stores). The WAIT half of the barrier comes in two forms (shard.cu picks):
 //   * one rank per process (torchrun): the signalling thread itself spins on the local flags, so the kernel retires
 //     with the complete replicated result — one launch per device and nothing else on the path;
 //   * one process driving several ranks: stream memory operations (cuStreamWaitValue32 on the local flags) enqueued
@@ -32,12 +32,12 @@ struct PeerSync {
     uint32_t *error;                       // sticky: an in-kernel wait gave up (a rank never arrived)
 };
 
-__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+__device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const uint32_t *p) {
     uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ uint64_t global_timer_ns() {
@@ -51,18 +51,21 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // (a few microseconds sooner than stream memory operations notice the flags). Only used when the process drives a
 // single rank, where nothing the host still has to do can be what the spinning thread waits for.
 __device__ __forceinline__ void peer_signal(const PeerSync &ps) {
+    // release pattern: ONE system-scope fence, then relaxed flag stores (a st.release per flag would pay the fence
+    // once per rank); acquire pattern on the other side: relaxed polls, one fence when all flags are in
     __threadfence_system();
-    for (int k = 0; k < ps.nflags; ++k) st_release_sys_u32(ps.flag_peer[k], ps.epoch);
+    for (int k = 0; k < ps.nflags; ++k) st_relaxed_sys_u32(ps.flag_peer[k], ps.epoch);
     if (!ps.wait_in_kernel) return;
     const uint64_t t0 = global_timer_ns();
     for (int k = 0; k < ps.nflags; ++k) {
-        while ((int32_t)(ld_acquire_sys_u32(ps.flag_local + k) - ps.epoch) < 0) {
+        while ((int32_t)(ld_relaxed_sys_u32(ps.flag_local + k) - ps.epoch) < 0) {
             if (global_timer_ns() - t0 > 20000000000ull) {  // 20 s: a rank never arrived; do not hang the GPU
                 *ps.error = 1;
                 return;
             }
         }
     }
+    __threadfence_system();
 }
 
 // Called by EVERY thread of EVERY CTA at the end of a kernel that may be a sharded launch. One system-scope fence

@@ -772,7 +772,18 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
                 p.parts = 1;
                 p.part_len = L;
                 int64_t ctas = (rc + kRedWarps - 1) / kRedWarps;
-                const int64_t cap = (int64_t)sms * 16;
+                int64_t cap = (int64_t)sms * 16;
+                if (sync.nflags > 0) {
+                    // sharded launch: ONE wave of CTAs. Every CTA ends with a system-scope fence that waits for its
+                    // peer stores to be acknowledged across NVLink (microseconds); with several waves that latency is
+                    // paid once per wave (measured at 8 GPUs: 48 us on top of a 21 us kernel with 4 waves).
+                    static const int occ = [] {
+                        int nb = 0;
+                        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, reduce_rows_kernel<Op>, kRedThreads, 0) != cudaSuccess || nb < 1) nb = 2;
+                        return nb;
+                    }();
+                    cap = (int64_t)sms * occ;
+                }
                 if (ctas > cap) ctas = cap;
                 p.peer = sync;
                 DN_LAUNCH((reduce_rows_kernel<Op>), (unsigned)ctas, kRedThreads, 0, p, op);
