@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(1024) scatter_scan_kernel(uint32_t *bin_start,
     if (threadIdx.x == 1023) bin_start[nbins] = part[1023];
 }
 
-template <bool PAIRS, class TS, class TA, int NDI, int NDO>
+// FINAL: the bins of this level are the fine bins: write the index inside the bin (u16); otherwise the full index.
+template <bool PAIRS, bool FINAL, class TS, class TA, int NDI, int NDO>
 __global__ void __launch_bounds__(kBinThreads) scatter_partition_kernel(const __grid_constant__ BinParams p) {
     extern __shared__ uint32_t sh_cur[];
     const uint32_t *mine = p.cta_hist + (uint64_t)blockIdx.x * p.nbins;
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(kBinThreads) scatter_partition_kernel(const __
         for (int j = 0; j < U; ++j)
             if (ok[j]) {
                 const uint32_t pos = atomicAdd(&sh_cur[lin[j] >> p.bin_log], 1u);
-                if constexpr (PAIRS) p.out_low[pos] = (uint16_t)(lin[j] & mask);
+                if constexpr (FINAL) p.out_low[pos] = (uint16_t)(lin[j] & mask);
                 else p.out_lin[pos] = lin[j];
                 vals[pos] = v[j];
             }
@@ -436,7 +437,7 @@ bool dense_row_major(const dn_tensor *t) {
 }
 
 // hist -> offsets -> scan -> partition for one level. `p` carries the level's bins, inputs and outputs.
-template <bool PAIRS, class TS, class TA>
+template <bool PAIRS, bool FINAL, class TS, class TA>
 dn_status scatter_partition_level(BinParams &p, int grid) {
     const size_t hist_smem = (size_t)p.nbins * 4;
     DN_GS_RANK_DISPATCH(p.gs.nd_it, p.gs.nd_other,
@@ -444,7 +445,7 @@ dn_status scatter_partition_level(BinParams &p, int grid) {
     DN_LAUNCH(scatter_offsets_kernel, (unsigned)((p.nbins + 255) / 256), 256, 0, p.cta_hist, p.bin_start, p.nbins, (uint32_t)grid);
     DN_LAUNCH(scatter_scan_kernel, 1, 1024, 0, p.bin_start, p.nbins);
     DN_GS_RANK_DISPATCH(p.gs.nd_it, p.gs.nd_other,
-                        DN_LAUNCH((scatter_partition_kernel<PAIRS, TS, TA, NDI, NDO>), grid, kBinThreads, hist_smem, p));
+                        DN_LAUNCH((scatter_partition_kernel<PAIRS, FINAL, TS, TA, NDI, NDO>), grid, kBinThreads, hist_smem, p));
     return launch_status("scatter partition kernels");
 }
 
@@ -455,9 +456,10 @@ dn_status scatter_binned(const GSParams &gs, const dn_tensor *acc, int64_t nt, b
     const int esz = (int)sizeof(TA);
     const uint32_t fine_log = esz == 8 ? 13 : 14;   // 64 KiB of accumulators per CTA
     const int64_t nfine = (nt + (1ll << fine_log) - 1) >> fine_log;
-    // DN_SCATTER_BINNED: 0 = never, 1 = always (parity tests at small sizes); default: large problems only
-    static const int mode = [] { const char *e = getenv("DN_SCATTER_BINNED"); return e ? atoi(e) : -1; }();
-    if (mode == 0 || nfine > kMaxBins || !dense_row_major(acc) || gs.n == 0 || nt == 0) return DN_OK;
+    // NOT the default yet (still slower than one warp-aggregated L2 atomic per element).
+    // DN_SCATTER_BINNED=1: always (the parity tests cover it at small sizes); =2: for large problems only (tools).
+    static const int mode = [] { const char *e = getenv("DN_SCATTER_BINNED"); return e ? atoi(e) : 0; }();
+    if (mode <= 0 || nfine > kMaxBins || !dense_row_major(acc) || gs.n == 0 || nt == 0) return DN_OK;
     if (mode != 1 && (gs.n < (1u << 22) || nt < (1ll << 20))) return DN_OK;
     // coarse bins: at most 64, each a whole number of fine bins (at most 128 of them)
     uint32_t coarse_log = fine_log;
@@ -499,7 +501,7 @@ dn_status scatter_binned(const GSParams &gs, const dn_tensor *acc, int64_t nt, b
             p.nbins = (uint32_t)ncoarse;
             p.bin_log = coarse_log;
             p.out_vals = static_cast<char *>(s_vals1);
-            st = scatter_partition_level<false, TS, TA>(p, grid);
+            st = scatter_partition_level<false, false, TS, TA>(p, grid);
             p.in_lin = p.out_lin;
             p.in_vals = p.out_vals;
         }
@@ -507,7 +509,8 @@ dn_status scatter_binned(const GSParams &gs, const dn_tensor *acc, int64_t nt, b
             p.nbins = (uint32_t)nfine;
             p.bin_log = fine_log;
             p.out_vals = static_cast<char *>(s_vals2);
-            st = two_level ? scatter_partition_level<true, TS, TA>(p, grid) : scatter_partition_level<false, TS, TA>(p, grid);
+            st = two_level ? scatter_partition_level<true, true, TS, TA>(p, grid)
+                           : scatter_partition_level<false, true, TS, TA>(p, grid);
         }
         if (st == DN_OK) {
             const int acc_grid = nfine < (int64_t)sm_count() * 3 ? (int)nfine : sm_count() * 3;

@@ -768,7 +768,10 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
             // f32 Max = 1.7 waves ran at 86 % of peak).
             const bool heavy = Op::ordered || sizeof(State) > 8;
             const bool enough_waves = rc >= (int64_t)sms * 64 * 4 || bytes <= 16384;
-            if (bytes <= 4096 || (heavy && rc >= warps_wanted && bytes <= 65536 && enough_waves)) {
+            // 1-byte elements (All / Any / CountTrue over bool rows): a 16 KiB row is only 8 load groups of a warp;
+            // split over a CTA every warp gets ONE group and the CTA's barriers and combine dominate (58-67 % of peak)
+            const bool small_elems = sizeof(typename Op::In) == 1 && bytes <= 32768 && rc >= warps_wanted / 2;
+            if (bytes <= 4096 || small_elems || (heavy && rc >= warps_wanted && bytes <= 65536 && enough_waves)) {
                 p.parts = 1;
                 p.part_len = L;
                 int64_t ctas = (rc + kRedWarps - 1) / kRedWarps;

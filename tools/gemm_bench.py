@@ -16,6 +16,11 @@ def main():
     dev = CudaTensor.dev()
     dev.Init(0)
     dev.SetStream(torch.cuda.current_stream().cuda_stream)
+    # usage: gemm_bench.py [tf32|fp32|strict] [case-name-substring]
+    mode = sys.argv[1] if len(sys.argv) > 1 else "tf32"
+    only = sys.argv[2] if len(sys.argv) > 2 else ""
+    dev.SetMathMode(mode)
+    print(f"math mode: {mode}")
     torch.backends.cuda.matmul.allow_tf32 = True
     cases = [
         ("fwd1  X[8192,784] . W1.T[784,4096]", 8192, 4096, 784, "NT"),
@@ -27,6 +32,8 @@ def main():
         ("sq    8192^3", 8192, 8192, 8192, "NT"),
     ]
     for name, M, N, K, lay in cases:
+        if only and only not in name:
+            continue
         if lay == "NT":
             ta, tb = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
             a, b = wrap(ta), wrap(tb).T

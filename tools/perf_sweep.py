@@ -145,6 +145,9 @@ def main():
     run("C3 f32 argMaxAxis1 262144x1000", nb + 262144 * 8, lambda: oi._fill_axis("ArgMaxLastAxis", 1, lg, True))
     run("C3 f32 maxAxis1 262144x1000", nb + 262144 * 4, lambda: om.FillMaxAxis(1, lg))
     run("C3 f32 sumAxis1 262144x1000", nb + 262144 * 4, lambda: om.FillSumAxis(1, lg))
+    _d = lambda t: t.Backend._d(t)
+    run("C3 f32 max+argmax ONE pass 262144x1000", nb + 262144 * 12,
+        lambda: dev.api.call("shard_minmax_arg_last_axis", None, 0, 1, _d(om), _d(oi), 0, _d(lg)))
     del tl, lg
 
     # C4
