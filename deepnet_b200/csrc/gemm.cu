@@ -22,6 +22,8 @@
 // float64 has no tcgen05 path: a shared-memory tiled SIMT kernel.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "ew_ops.cuh"
 
 using namespace dn;
@@ -320,6 +322,232 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// cta_group::2: a CTA PAIR (cluster of 2, two SMs of one TPC) computes one 256 x 256 tile with M = 256 MMAs.
+// Each CTA stages its own 128 rows of A and HALF of B (128 of the 256 N rows) — 32 KiB per stage instead of the
+// 48 KiB a single CTA needs for a 128 x 256 tile — and the tensor core reads both halves of B out of both SMs'
+// shared memory: per SM the operand traffic through shared memory is 2/3 of the one-CTA kernel's per flop, which is
+// what caps that kernel at ~84 % of cuBLAS. Accumulators: each CTA's TMEM holds its 128 rows x 256
+// columns (two stages = all 512 columns).
+// Protocol (PTX forms as in CUTLASS cute/arch/copy_sm100_tma.hpp, mma_sm100_umma.hpp, cutlass/arch/barrier.h):
+//   - both CTAs issue their TMA loads with .cta_group::2, completing transaction bytes on the LEADER's (rank 0) full
+//     barrier (address with the peer bit cleared); the leader alone arms it with expect_tx for both CTAs' bytes;
+//   - the leader's MMA thread issues tcgen05.mma.cta_group::2; tcgen05.commit.cta_group::2 ... multicast::cluster
+//     arrives on the empty / tmem_full barriers of BOTH CTAs;
+//   - the epilogue warps of both CTAs arrive on the LEADER's tmem_empty barrier (8 arrivals).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // cute::Sm100MmaPeerBitMask
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, uint64_t *leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {  // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {  // from either CTA, on the leader's barrier
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+constexpr int kBN2 = 256;  // tile N of the pair; each CTA stages kBN2 / 2 rows of B
+
+// Tile order: groups of kGroupM tile rows are walked column by column, so that the ~74 tiles in flight cover a
+// compact (8 x ~9) patch of C and share their A and B panels in L2 (row-major order makes every wave read ALL of A).
+constexpr int kGroupM = 8;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int &m_blk, int &n_blk) {
+    const int per_group = kGroupM * tiles_n;
+    const int group = tile / per_group, in_group = tile - group * per_group;
+    const int m_first = group * kGroupM;
+    const int rows = tiles_m - m_first < kGroupM ? tiles_m - m_first : kGroupM;
+    n_blk = in_group / rows;
+    m_blk = m_first + (in_group - n_blk * rows);
+}
+
+struct GemmCfg2 {
+    static constexpr int kStageBytes = (kBM + kBN2 / 2) * kBK * 4;  // 32 KiB per CTA
+    static constexpr int kStages = 6;
+    static constexpr int kTmemCols = 2 * kBN2;
+    static constexpr int kEpiBytes = 4 * 32 * 33 * 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiBytes;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+    gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+    using Cfg = GemmCfg2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t *full = bars, *empty = bars + Cfg::kStages;
+    uint64_t *tmem_full = bars + 2 * Cfg::kStages, *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *epi = reinterpret_cast<float *>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int num_tiles = p.tiles_m * p.tiles_n;  // tiles of 256 x 256
+    const int num_kb = (p.K + kBK - 1) / kBK;
+
+    if (warp == 1 && elect_one()) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps of each CTA
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)Cfg::kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += npairs) {
+                int m_blk, n_blk;
+                tile_coords(tile, p.tiles_m, p.tiles_n, m_blk, n_blk);
+                const int m0 = m_blk * 2 * kBM + (int)rank * kBM, n0 = n_blk * kBN2 + (int)rank * (kBN2 / 2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t *sa = smem + stage * Cfg::kStageBytes;
+                    uint8_t *sb = sa + kBM * kBK * 4;
+                    if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+                    if constexpr (A_MN) {
+#pragma unroll
+                        for (int blk = 0; blk < kBM / 32; ++blk)
+                            tma_load_2d_2sm(sa + blk * 4096, &map_a, &full[stage], m0 + blk * 32, kb * kBK);
+                    } else {
+                        tma_load_2d_2sm(sa, &map_a, &full[stage], kb * kBK, m0);
+                    }
+                    if constexpr (B_MN) {
+#pragma unroll
+                        for (int blk = 0; blk < kBN2 / 2 / 32; ++blk)
+                            tma_load_2d_2sm(sb + blk * 4096, &map_b, &full[stage], n0 + blk * 32, kb * kBK);
+                    } else {
+                        tma_load_2d_2sm(sb, &map_b, &full[stage], kb * kBK, n0);
+                    }
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && elect_one()) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(kBN2 >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += npairs) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_c = tmem_base + (uint32_t)(acc * kBN2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t sb = sa + kBM * kBK * 4;
+                    const uint64_t da = A_MN ? make_mnmajor_sw128_desc(sa) : make_kmajor_sw128_desc(sa);
+                    const uint64_t db = B_MN ? make_mnmajor_sw128_desc(sb) : make_kmajor_sw128_desc(sb);
+                    constexpr uint64_t stepA = A_MN ? (1024 >> 4) : (32 >> 4), stepB = B_MN ? (1024 >> 4) : (32 >> 4);
+#pragma unroll
+                    for (int k = 0; k < kBK / 8; ++k)
+                        umma_tf32_2sm(tmem_c, da + (uint64_t)k * stepA, db + (uint64_t)k * stepB, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit_2sm(&empty[stage]);
+                    if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc]);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool vec_ok = p.ldc_n == 1 && (p.ldc_m % 4) == 0 && (reinterpret_cast<uintptr_t>(p.c) & 15) == 0;
+        for (int tile = pair; tile < num_tiles; tile += npairs) {
+            int m_blk, n_blk;
+            tile_coords(tile, p.tiles_m, p.tiles_n, m_blk, n_blk);
+            const int mbase = m_blk * 2 * kBM + (int)rank * kBM;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int row = mbase + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBN2);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kBN2; c0 += 32) {
+                const int col = n_blk * kBN2 + c0;
+                if (col >= p.N) break;  // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + (uint32_t)c0, r);
+                if (vec_ok && col + 32 <= p.N) {
+                    float *blk = epi + (warp - 2) * (32 * 33);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) blk[lane * 33 + j] = __uint_as_float(r[j]);
+                    __syncwarp();
+                    const int cg = (lane & 7) * 4;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + (lane >> 3);
+                        const int grow = mbase + quarter * 32 + rr;
+                        if (grow < p.M) {
+                            const float *sp = blk + rr * 33 + cg;
+                            *reinterpret_cast<float4 *>(p.c + (int64_t)grow * p.ldc_m + col + cg) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                        }
+                    }
+                    __syncwarp();
+                } else if (row < p.M) {
+                    float *crow = p.c + (int64_t)row * p.ldc_m + (int64_t)col * p.ldc_n;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col + j < p.N) crow[(int64_t)j * p.ldc_n] = __uint_as_float(r[j]);
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Host side of the tf32 path
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -412,6 +640,22 @@ dn_status launch_tf32(const CUtensorMap &ma, const CUtensorMap &mb, const CUtens
     return launch_status("tcgen05 GEMM kernel");
 }
 
+template <bool A_MN, bool B_MN>
+dn_status launch_tf32_2cta(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p) {
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    DN_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
+        DN_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32_2cta_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg2::kSmemBytes));
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
+    }
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+    DN_LAUNCH((gemm_tf32_2cta_kernel<A_MN, B_MN>), 2 * pairs, kGemmThreads, GemmCfg2::kSmemBytes, ma, mb, p);
+    return launch_status("tcgen05 2-CTA GEMM kernel");
+}
+
 template <int BN>
 dn_status launch_tf32_major(bool a_mn, bool b_mn, const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p) {
     if (a_mn) return b_mn ? launch_tf32<BN, true, true>(ma, mb, ma, mb, p) : launch_tf32<BN, true, false>(ma, mb, ma, mb, p);
@@ -442,6 +686,22 @@ dn_status gemm_f32_tf32(float *c, int64_t cm, int64_t cn, const float *a, int64_
     p.c = c; p.ldc_m = cm; p.ldc_n = cn;
     p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K;
     const int BN = N <= 32 ? 32 : (N <= 128 ? 128 : 256);
+    // large problems: CTA pairs on 256 x 256 tiles (DN_GEMM_2CTA=0, a test hook, keeps the one-CTA kernel)
+    static const bool allow_2cta = [] { const char *e = getenv("DN_GEMM_2CTA"); return !(e && e[0] == '0'); }();
+    const bool two_cta = allow_2cta && M >= 512 && N >= 256;
+    if (st == DN_OK && two_cta) {
+        p.tiles_m = (int32_t)((M + 2 * kBM - 1) / (2 * kBM));
+        p.tiles_n = (int32_t)((N + kBN2 - 1) / kBN2);
+        st = a_mn ? make_map(&ma, A.ptr, K, A.rows, A.ks, kBK, true) : make_map(&ma, A.ptr, A.rows, K, A.rs, kBM);
+        if (st == DN_OK) st = b_mn ? make_map(&mb, B.ptr, K, B.rows, B.ks, kBK, true) : make_map(&mb, B.ptr, B.rows, K, B.rs, kBN2 / 2);
+        if (st == DN_OK) {
+            if (a_mn) st = b_mn ? launch_tf32_2cta<true, true>(ma, mb, p) : launch_tf32_2cta<true, false>(ma, mb, p);
+            else st = b_mn ? launch_tf32_2cta<false, true>(ma, mb, p) : launch_tf32_2cta<false, false>(ma, mb, p);
+        }
+        scratch_free(sa);
+        scratch_free(sb);
+        return st;
+    }
     p.tiles_m = (int32_t)((M + kBM - 1) / kBM);
     p.tiles_n = (int32_t)((N + BN - 1) / BN);
     if (st == DN_OK) st = a_mn ? make_map(&ma, A.ptr, K, A.rows, A.ks, kBK, true) : make_map(&ma, A.ptr, A.rows, K, A.rs, kBM);

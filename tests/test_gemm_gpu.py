@@ -287,3 +287,39 @@ def test_tf32_mode_is_opt_in(cuda_dev, tf32_mode):
     got = (CudaTensor.ofNumpy(a) @ CudaTensor.ofNumpy(b)).toNumpy().astype(np.float64)
     rel = np.linalg.norm(got - want) / np.linalg.norm(want)
     assert 1e-4 < rel <= 1e-2, rel
+
+
+TF32_SHAPES = [(512, 256, 64), (512, 512, 32), (1000, 300, 777), (1024, 1024, 1024), (777, 1111, 333), (8192, 4096, 784),
+               (2048, 4096, 4096), (513, 257, 100)]
+
+
+@pytest.mark.parametrize("M,N,K", TF32_SHAPES)
+def test_tf32_mode_shapes(cuda_dev, tf32_mode, M, N, K):
+    """DN_MATH_TF32 on shapes that take the CTA-pair kernel (M >= 512, N >= 256: 256 x 256 tiles, cta_group::2) with
+    full, partial and odd tiles; rel 1e-2 (north_star), per element on the scale of the dot product's terms."""
+    rng = np.random.default_rng(53)
+    a, b = rand_array(rng, (M, K), dtypes.DN_F32, -1, 1), rand_array(rng, (K, N), dtypes.DN_F32, -1, 1)
+    (ha, ca), (hb, cb) = pair(a), pair(b)
+    check_mm(ha @ hb, ca @ cb, a, b, dtypes.DN_F32, f"tf32 {M}x{K} . {K}x{N}")
+
+
+def test_tf32_mode_layouts(cuda_dev, tf32_mode):
+    """Every operand layout of the MLP step through the CTA-pair kernel: X.W^T (K-major both), dY.W (B N-major),
+    dY^T.X (A M-major), both transposed, sliced views (repacked), a column-major target."""
+    rng = np.random.default_rng(54)
+    M, N, K = 768, 512, 264
+    a, bt = rand_array(rng, (M, K), dtypes.DN_F32, -1, 1), rand_array(rng, (N, K), dtypes.DN_F32, -1, 1)
+    (ha, ca), (hbt, cbt) = pair(a), pair(bt)
+    check_mm(ha @ hbt.T, ca @ cbt.T, a, bt.T, dtypes.DN_F32, "A . B^T")
+    at, b = rand_array(rng, (K, M), dtypes.DN_F32, -1, 1), rand_array(rng, (K, N), dtypes.DN_F32, -1, 1)
+    (hat, cat), (hb, cb) = pair(at), pair(b)
+    check_mm(hat.T @ hb, cat.T @ cb, at.T, b, dtypes.DN_F32, "A^T . B")
+    check_mm(ha @ hb, ca @ cb, a, b, dtypes.DN_F32, "A . B")
+    check_mm(hat.T @ hbt.T, cat.T @ cbt.T, at.T, bt.T, dtypes.DN_F32, "A^T . B^T")
+    check_mm(ha[3:700, 5:200] @ hb[5:200, 1:400], ca[3:700, 5:200] @ cb[5:200, 1:400], a[3:700, 5:200], b[5:200, 1:400],
+             dtypes.DN_F32, "sliced")
+    ht = Tensor.empty((M, N), dtypes.DN_F32, ha.Dev, order="F")
+    ct = Tensor.empty((M, N), dtypes.DN_F32, ca.Dev, order="F")
+    ht.FillDot(ha, hb)
+    ct.FillDot(ca, cb)
+    check_mm(ht, ct, a, b, dtypes.DN_F32, "column-major target")
