@@ -128,6 +128,10 @@ struct GemmParams {
     int64_t ldc_m, ldc_n;  // element strides of C
     int32_t M, N, K;
     int32_t tiles_m, tiles_n;
+    // batched launch of the CTA-pair kernel: tile index = batch * tiles_m * tiles_n + tile in matrix
+    int32_t nbatch = 1;
+    int32_t a_batched = 0, b_batched = 0;  // 0: the operand is shared by all batch elements (broadcast)
+    int64_t c_batch = 0;                   // element stride of C between batch elements
 };
 
 // SPLIT (3xTF32, fp32-accurate): a stage also holds the low-order tf32 halves of both operands.
@@ -352,6 +356,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *ma
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_2sm(void *dst, const CUtensorMap *map, uint64_t *leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -406,7 +416,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int num_tiles = p.tiles_m * p.tiles_n;  // tiles of 256 x 256
+    const int tiles_per_mat = p.tiles_m * p.tiles_n;  // tiles of 256 x 256
+    const int num_tiles = tiles_per_mat * p.nbatch;   // the maps are 3-D: (k, row, batch element)
     const int num_kb = (p.K + kBK - 1) / kBK;
 
     if (warp == 1 && elect_one()) {
@@ -436,7 +447,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
             uint32_t phase = 0;
             for (int tile = pair; tile < num_tiles; tile += npairs) {
                 int m_blk, n_blk;
-                tile_coords(tile, p.tiles_m, p.tiles_n, m_blk, n_blk);
+                const int bi = tile / tiles_per_mat;
+                tile_coords(tile - bi * tiles_per_mat, p.tiles_m, p.tiles_n, m_blk, n_blk);
+                const int ba = p.a_batched ? bi : 0, bb = p.b_batched ? bi : 0;
                 const int m0 = m_blk * 2 * kBM + (int)rank * kBM, n0 = n_blk * kBN2 + (int)rank * (kBN2 / 2);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -446,16 +459,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                     if constexpr (A_MN) {
 #pragma unroll
                         for (int blk = 0; blk < kBM / 32; ++blk)
-                            tma_load_2d_2sm(sa + blk * 4096, &map_a, &full[stage], m0 + blk * 32, kb * kBK);
+                            tma_load_3d_2sm(sa + blk * 4096, &map_a, &full[stage], m0 + blk * 32, kb * kBK, ba);
                     } else {
-                        tma_load_2d_2sm(sa, &map_a, &full[stage], kb * kBK, m0);
+                        tma_load_3d_2sm(sa, &map_a, &full[stage], kb * kBK, m0, ba);
                     }
                     if constexpr (B_MN) {
 #pragma unroll
                         for (int blk = 0; blk < kBN2 / 2 / 32; ++blk)
-                            tma_load_2d_2sm(sb + blk * 4096, &map_b, &full[stage], n0 + blk * 32, kb * kBK);
+                            tma_load_3d_2sm(sb + blk * 4096, &map_b, &full[stage], n0 + blk * 32, kb * kBK, bb);
                     } else {
-                        tma_load_2d_2sm(sb, &map_b, &full[stage], kb * kBK, n0);
+                        tma_load_3d_2sm(sb, &map_b, &full[stage], kb * kBK, n0, bb);
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -495,10 +508,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
         const int quarter = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const bool vec_ok = p.ldc_n == 1 && (p.ldc_m % 4) == 0 && (reinterpret_cast<uintptr_t>(p.c) & 15) == 0;
+        const bool vec_ok = p.ldc_n == 1 && (p.ldc_m % 4) == 0 && (p.c_batch % 4) == 0 && (reinterpret_cast<uintptr_t>(p.c) & 15) == 0;
         for (int tile = pair; tile < num_tiles; tile += npairs) {
             int m_blk, n_blk;
-            tile_coords(tile, p.tiles_m, p.tiles_n, m_blk, n_blk);
+            const int bi = tile / tiles_per_mat;
+            tile_coords(tile - bi * tiles_per_mat, p.tiles_m, p.tiles_n, m_blk, n_blk);
+            float *cmat = p.c + (int64_t)bi * p.c_batch;
             const int mbase = m_blk * 2 * kBM + (int)rank * kBM;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
@@ -522,12 +537,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                         const int grow = mbase + quarter * 32 + rr;
                         if (grow < p.M) {
                             const float *sp = blk + rr * 33 + cg;
-                            *reinterpret_cast<float4 *>(p.c + (int64_t)grow * p.ldc_m + col + cg) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                            *reinterpret_cast<float4 *>(cmat + (int64_t)grow * p.ldc_m + col + cg) = make_float4(sp[0], sp[1], sp[2], sp[3]);
                         }
                     }
                     __syncwarp();
                 } else if (row < p.M) {
-                    float *crow = p.c + (int64_t)row * p.ldc_m + (int64_t)col * p.ldc_n;
+                    float *crow = cmat + (int64_t)row * p.ldc_m + (int64_t)col * p.ldc_n;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (col + j < p.N) crow[(int64_t)j * p.ldc_n] = __uint_as_float(r[j]);
@@ -581,6 +596,24 @@ dn_status make_map(CUtensorMap *map, const float *base, int64_t outer, int64_t i
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(DN_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return DN_OK;
+}
+
+// 3-D fp32 tensor map for the batched CTA-pair kernel: (inner, outer, batch); box = {32, box_outer, 1}. A shared
+// (broadcast) operand has nbatch = 1 and is always addressed with batch coordinate 0.
+dn_status make_map3(CUtensorMap *map, const float *base, int64_t outer, int64_t inner, int64_t pitch, int box_outer,
+                    bool mn_major, int64_t nbatch, int64_t batch_stride) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(DN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(nbatch > 0 ? nbatch : 1)};
+    const int64_t bs = nbatch > 1 ? batch_stride : pitch * outer;  // unused when there is one batch element
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)bs * 4};
+    cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_outer, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(DN_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with code %d", (int)r);
     return DN_OK;
 }
 
@@ -650,8 +683,8 @@ dn_status launch_tf32_2cta(const CUtensorMap &ma, const CUtensorMap &mb, const G
                                          GemmCfg2::kSmemBytes));
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
-    const int tiles = p.tiles_m * p.tiles_n;
-    const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n * p.nbatch;
+    const int pairs = tiles < sm_count() / 2 ? (int)tiles : sm_count() / 2;
     DN_LAUNCH((gemm_tf32_2cta_kernel<A_MN, B_MN>), 2 * pairs, kGemmThreads, GemmCfg2::kSmemBytes, ma, mb, p);
     return launch_status("tcgen05 2-CTA GEMM kernel");
 }
@@ -663,8 +696,17 @@ dn_status launch_tf32_major(bool a_mn, bool b_mn, const CUtensorMap &ma, const C
 }
 
 // C[M,N] (strides cm, cn) = A[M,K] (am, ak) · B[K,N] (bk, bn), fp32 operands read as tf32 (DN_MATH_TF32).
+// large problems: CTA pairs on 256 x 256 tiles (DN_GEMM_2CTA=0, a test hook, keeps the one-CTA kernel)
+bool tf32_pair_eligible(int64_t M, int64_t N) {
+    static const bool allow = [] { const char *e = getenv("DN_GEMM_2CTA"); return !(e && e[0] == '0'); }();
+    return allow && M >= 512 && N >= 256;
+}
+
+// nbatch > 1 (CTA-pair kernel only): ONE launch for all batch elements; *_bs are the element strides between batch
+// elements, 0 = the operand is shared (broadcast batch dims).
 dn_status gemm_f32_tf32(float *c, int64_t cm, int64_t cn, const float *a, int64_t am, int64_t ak, const float *b, int64_t bk,
-                   int64_t bn, int64_t M, int64_t N, int64_t K) {
+                   int64_t bn, int64_t M, int64_t N, int64_t K, int64_t nbatch = 1, int64_t c_bs = 0, int64_t a_bs = 0,
+                   int64_t b_bs = 0) {
     if (M == 0 || N == 0) return DN_OK;
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return set_error(DN_ERR_UNSUPPORTED, "MatMatDot: extent exceeds 2^31-1");
     if (K == 0) {  // empty sum: C = 0
@@ -686,14 +728,21 @@ dn_status gemm_f32_tf32(float *c, int64_t cm, int64_t cn, const float *a, int64_
     p.c = c; p.ldc_m = cm; p.ldc_n = cn;
     p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K;
     const int BN = N <= 32 ? 32 : (N <= 128 ? 128 : 256);
-    // large problems: CTA pairs on 256 x 256 tiles (DN_GEMM_2CTA=0, a test hook, keeps the one-CTA kernel)
-    static const bool allow_2cta = [] { const char *e = getenv("DN_GEMM_2CTA"); return !(e && e[0] == '0'); }();
-    const bool two_cta = allow_2cta && M >= 512 && N >= 256;
+    const bool two_cta = tf32_pair_eligible(M, N);
+    if (nbatch > 1 && (!two_cta || sa || sb))
+        return set_error(DN_ERR_INVALID_ARG, "internal: batched tf32 launch needs the CTA-pair kernel and in-place operands");
     if (st == DN_OK && two_cta) {
         p.tiles_m = (int32_t)((M + 2 * kBM - 1) / (2 * kBM));
         p.tiles_n = (int32_t)((N + kBN2 - 1) / kBN2);
-        st = a_mn ? make_map(&ma, A.ptr, K, A.rows, A.ks, kBK, true) : make_map(&ma, A.ptr, A.rows, K, A.rs, kBM);
-        if (st == DN_OK) st = b_mn ? make_map(&mb, B.ptr, K, B.rows, B.ks, kBK, true) : make_map(&mb, B.ptr, B.rows, K, B.rs, kBN2 / 2);
+        p.nbatch = (int32_t)nbatch;
+        p.a_batched = a_bs != 0;
+        p.b_batched = b_bs != 0;
+        p.c_batch = c_bs;
+        const int64_t na = a_bs != 0 ? nbatch : 1, nb = b_bs != 0 ? nbatch : 1;
+        st = a_mn ? make_map3(&ma, A.ptr, K, A.rows, A.ks, kBK, true, na, a_bs) : make_map3(&ma, A.ptr, A.rows, K, A.rs, kBM, false, na, a_bs);
+        if (st == DN_OK)
+            st = b_mn ? make_map3(&mb, B.ptr, K, B.rows, B.ks, kBK, true, nb, b_bs)
+                      : make_map3(&mb, B.ptr, B.rows, K, B.rs, kBN2 / 2, false, nb, b_bs);
         if (st == DN_OK) {
             if (a_mn) st = b_mn ? launch_tf32_2cta<true, true>(ma, mb, p) : launch_tf32_2cta<true, false>(ma, mb, p);
             else st = b_mn ? launch_tf32_2cta<false, true>(ma, mb, p) : launch_tf32_2cta<false, false>(ma, mb, p);
@@ -737,7 +786,8 @@ struct SimtBatch {
 template <class T>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(T *c, int64_t cm, int64_t cn, const T *a, int64_t am, int64_t ak,
                                                        const T *b, int64_t bk, int64_t bn, int M, int N, int K,
-                                                       const __grid_constant__ SimtBatch batch) {
+                                                       const __grid_constant__ SimtBatch batch, const int *guard) {
+    if (guard && *guard == 0) return;  // conditional re-run (3xTF32 with non-finite inputs): nothing to do
     __shared__ T sa[kDK][kDT + 1], sb[kDK][kDT + 1];
     {
         uint32_t rem = blockIdx.z + batch.z0;
@@ -793,7 +843,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(T *c, int64_t cm, int64_
 template <class T>
 dn_status gemm_simt(T *c, int64_t cm, int64_t cn, const T *a, int64_t am, int64_t ak, const T *b, int64_t bk, int64_t bn,
                     int64_t M, int64_t N, int64_t K, int nbd, const int64_t *bshape, const int64_t *bt, const int64_t *ba,
-                    const int64_t *bb) {
+                    const int64_t *bb, const int *guard = nullptr) {
     if (M == 0 || N == 0) return DN_OK;
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return set_error(DN_ERR_UNSUPPORTED, "MatMatDot: extent exceeds 2^31-1");
     SimtBatch batch;
@@ -816,7 +866,7 @@ dn_status gemm_simt(T *c, int64_t cm, int64_t cn, const T *a, int64_t am, int64_
     for (int64_t z0 = 0; z0 < nbatch; z0 += 65535) {
         grid.z = (unsigned)(nbatch - z0 < 65535 ? nbatch - z0 : 65535);
         batch.z0 = (uint32_t)z0;
-        DN_LAUNCH((gemm_simt_kernel<T>), grid, 256, 0, c, cm, cn, a, am, ak, b, bk, bn, (int)M, (int)N, (int)K, batch);
+        DN_LAUNCH((gemm_simt_kernel<T>), grid, 256, 0, c, cm, cn, a, am, ak, b, bk, bn, (int)M, (int)N, (int)K, batch, guard);
     }
     return launch_status("SIMT GEMM kernel");
 }
@@ -834,9 +884,11 @@ __device__ __forceinline__ float to_tf32(float x) {  // round to nearest, ties a
 
 // hi = tf32(x), lo = tf32(x - hi) for a K-major [rows, K] operand (row pitch `rs` elements) into dense [rows, pitch]
 // arrays. Both outputs are exactly representable in tf32, so whatever the tensor core does with the low 13 bits of
-// its inputs (it ignores them) does not matter. Non-finite x: hi = x, lo = 0.
+// its inputs (it ignores them) does not matter. Non-finite x: hi = x, lo = 0, and *nonfinite is raised: an infinity
+// times the OTHER operand's low half can come out with the wrong sign (inf - inf = NaN where the true product is
+// +-inf), so such a product is recomputed by the exact kernel (gemm_f32_split).
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float *src, int64_t rs, int64_t rows, int64_t K, float *hi,
-                                                        float *lo, int64_t pitch) {
+                                                        float *lo, int64_t pitch, int *nonfinite) {
     const int64_t n4 = pitch / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * n4; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / n4, k = (i - r * n4) * 4;
@@ -854,6 +906,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *src, int64
         l.y = isfinite(v.y) ? to_tf32(v.y - h.y) : 0.f;
         l.z = isfinite(v.z) ? to_tf32(v.z - h.z) : 0.f;
         l.w = isfinite(v.w) ? to_tf32(v.w - h.w) : 0.f;
+        if (!(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w))) *nonfinite = 1;
         *reinterpret_cast<float4 *>(hi + r * pitch + k) = h;
         *reinterpret_cast<float4 *>(lo + r * pitch + k) = l;
     }
@@ -861,7 +914,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *src, int64
 
 // Makes `o` K-major (in place when it already is, else through the transposing copy) and splits it; on return
 // hi / lo are dense [rows, pitch] scratch arrays.
-dn_status split_operand(Operand2D o, float **hi, float **lo, int64_t *pitch, void **scratch_hi, void **scratch_lo) {
+dn_status split_operand(Operand2D o, float **hi, float **lo, int64_t *pitch, void **scratch_hi, void **scratch_lo, int *nonfinite) {
     void *packed = nullptr;
     dn_status st = DN_OK;
     if (!tma_ready(o)) st = repack_kmajor(o, &packed);
@@ -874,7 +927,7 @@ dn_status split_operand(Operand2D o, float **hi, float **lo, int64_t *pitch, voi
         int64_t ctas = (o.rows * (*pitch / 4) + 255) / 256;
         const int64_t cap = (int64_t)sm_count() * 8;
         if (ctas > cap) ctas = cap;
-        DN_LAUNCH(split_tf32_kernel, (unsigned)ctas, 256, 0, o.ptr, o.rs, o.rows, o.K, *hi, *lo, *pitch);
+        DN_LAUNCH(split_tf32_kernel, (unsigned)ctas, 256, 0, o.ptr, o.rs, o.rows, o.K, *hi, *lo, *pitch, nonfinite);
         st = launch_status("tf32 split kernel");
     }
     scratch_free(packed);
@@ -886,9 +939,13 @@ dn_status gemm_f32_split(float *c, int64_t cm, int64_t cn, const float *a, int64
     Operand2D A{a, M, K, am, ak}, B{b, N, K, bn, bk};  // B viewed as [N, K]
     float *ahi = nullptr, *alo = nullptr, *bhi = nullptr, *blo = nullptr;
     int64_t pa = 0, pb = 0;
-    void *s0 = nullptr, *s1 = nullptr, *s2 = nullptr, *s3 = nullptr;
-    dn_status st = split_operand(A, &ahi, &alo, &pa, &s0, &s1);
-    if (st == DN_OK) st = split_operand(B, &bhi, &blo, &pb, &s2, &s3);
+    void *s0 = nullptr, *s1 = nullptr, *s2 = nullptr, *s3 = nullptr, *s_flag = nullptr;
+    dn_status st = scratch_alloc(sizeof(int), &s_flag);
+    if (st != DN_OK) return st;
+    int *nonfinite = static_cast<int *>(s_flag);
+    cudaMemsetAsync(nonfinite, 0, sizeof(int), current_stream());
+    st = split_operand(A, &ahi, &alo, &pa, &s0, &s1, nonfinite);
+    if (st == DN_OK) st = split_operand(B, &bhi, &blo, &pb, &s2, &s3, nonfinite);
     CUtensorMap ma, mb, mal, mbl;
     GemmParams p;
     p.c = c; p.ldc_m = cm; p.ldc_n = cn;
@@ -903,10 +960,14 @@ dn_status gemm_f32_split(float *c, int64_t cm, int64_t cn, const float *a, int64
     if (st == DN_OK)
         st = BN == 32 ? launch_tf32<32, false, false, true>(ma, mb, mal, mbl, p)
                       : launch_tf32<128, false, false, true>(ma, mb, mal, mbl, p);
+    // an operand held an infinity or a NaN: the exact kernel recomputes the product (its launch returns at once otherwise)
+    if (st == DN_OK)
+        st = gemm_simt<float>(c, cm, cn, a, am, ak, b, bk, bn, M, N, K, 0, nullptr, nullptr, nullptr, nullptr, nonfinite);
     scratch_free(s0);
     scratch_free(s1);
     scratch_free(s2);
     scratch_free(s3);
+    scratch_free(s_flag);
     return st;
 }
 
@@ -1196,6 +1257,35 @@ dn_status dn_batched_mat_mat_dot(const dn_tensor *t, const dn_tensor *a, const d
                                  reinterpret_cast<const double *>(data_ptr(a)), a->stride[nd - 2], a->stride[nd - 1],
                                  reinterpret_cast<const double *>(data_ptr(b)), b->stride[nd - 2], b->stride[nd - 1], M, N, K,
                                  nbd, bshape, bt, ba, bb);
+    }
+    // Large float32 batch elements in tf32 mode: ONE persistent launch of the CTA-pair kernel over all (batch, tile)
+    // pairs through 3-D tensor maps (the reference: one cublasSgemmBatched call, CudaBackend.fs:426-449), when the
+    // batch dims of every operand collapse to a single stride (or are all broadcast) and the matrices are TMA-ready.
+    if (nbatch > 1 && t->dtype == DN_F32 && g_math_mode.load(std::memory_order_relaxed) == DN_MATH_TF32 &&
+        tf32_pair_eligible(M, N) && nbatch < (1ll << 20)) {
+        auto collapse = [&](const dn_tensor *x, int64_t *bs) {  // single batch stride, 0 = broadcast; false = neither
+            bool all_zero = true;
+            for (int d = 0; d < nd - 2; ++d)
+                if (x->shape[d] > 1 && x->stride[d] != 0) all_zero = false;
+            if (all_zero) { *bs = 0; return true; }
+            int64_t expect = -1;
+            for (int d = nd - 3; d >= 0; --d) {
+                if (x->shape[d] == 1) continue;
+                if (expect < 0) *bs = x->stride[d];
+                else if (x->stride[d] != expect) return false;
+                expect = x->stride[d] * x->shape[d];
+            }
+            return *bs > 0;
+        };
+        int64_t cbs = 0, abs_ = 0, bbs = 0;
+        const float *ap = reinterpret_cast<const float *>(data_ptr(a)), *bp = reinterpret_cast<const float *>(data_ptr(b));
+        Operand2D A{ap, M, K, a->stride[nd - 2], a->stride[nd - 1]}, B{bp, N, K, b->stride[nd - 1], b->stride[nd - 2]};
+        const bool a_ok = tma_ready(A) || tma_ready_mn(A), b_ok = tma_ready(B) || tma_ready_mn(B);
+        if (a_ok && b_ok && collapse(t, &cbs) && cbs > 0 && collapse(a, &abs_) && collapse(b, &bbs) && abs_ % 4 == 0 &&
+            bbs % 4 == 0)
+            return gemm_f32_tf32(reinterpret_cast<float *>(data_ptr(t)), t->stride[nd - 2], t->stride[nd - 1], ap,
+                                 a->stride[nd - 2], a->stride[nd - 1], bp, b->stride[nd - 2], b->stride[nd - 1], M, N, K, nbatch,
+                                 cbs, abs_, bbs);
     }
     for (int64_t bi = 0; bi < nbatch; ++bi) {
         int64_t rem = bi, to = 0, ao = 0, bo = 0;

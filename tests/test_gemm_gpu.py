@@ -323,3 +323,33 @@ def test_tf32_mode_layouts(cuda_dev, tf32_mode):
     ht.FillDot(ha, hb)
     ct.FillDot(ca, cb)
     check_mm(ht, ct, a, b, dtypes.DN_F32, "column-major target")
+
+
+def test_tf32_batched_one_launch(cuda_dev, tf32_mode):
+    """BatchedMatMatDot with LARGE batch elements in tf32 mode is one persistent launch of the CTA-pair kernel over
+    3-D tensor maps (the reference: one cublasSgemmBatched call, CudaBackend.fs:426-449): plain batches, a shared
+    (broadcast) right operand, two batch dims, a transposed operand — each against the per-element 2-D call."""
+    rng = np.random.default_rng(55)
+    a = rand_array(rng, (3, 2, 512, 520), dtypes.DN_F32, -1, 1)      # 2^27.02 multiply-adds per element
+    b = rand_array(rng, (3, 2, 520, 512), dtypes.DN_F32, -1, 1)
+    (ha, ca), (hb, cb) = pair(a), pair(b)
+    n0 = cuda_dev.LaunchCount()
+    cc = ca @ cb
+    assert cuda_dev.LaunchCount() - n0 == 1, "one launch for the whole batch"
+    hc = ha @ hb
+    for i in range(3):
+        for j in range(2):
+            check_mm(hc[i, j], cc[i, j], a[i, j], b[i, j], dtypes.DN_F32, f"batch {i},{j}")
+    b1 = rand_array(rng, (1, 1, 520, 512), dtypes.DN_F32, -1, 1)
+    hb1, cb1 = pair(b1)
+    n0 = cuda_dev.LaunchCount()
+    cc = ca @ cb1.broadcastTo((3, 2, 520, 512))
+    assert cuda_dev.LaunchCount() - n0 == 1
+    hc = ha @ hb1.broadcastTo((3, 2, 520, 512))
+    check_mm(hc[2, 1], cc[2, 1], a[2, 1], b1[0, 0], dtypes.DN_F32, "shared right operand")
+    check_mm(hc[0, 0], cc[0, 0], a[0, 0], b1[0, 0], dtypes.DN_F32, "shared right operand [0,0]")
+    bt = rand_array(rng, (3, 2, 512, 520), dtypes.DN_F32, -1, 1)
+    hbt, cbt = pair(bt)
+    cc = ca @ cbt.swapDim(2, 3)
+    hc = ha @ hbt.swapDim(2, 3)
+    check_mm(hc[1, 1], cc[1, 1], a[1, 1], bt[1, 1].T, dtypes.DN_F32, "transposed right operand")
