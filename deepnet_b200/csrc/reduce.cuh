@@ -768,10 +768,9 @@ dn_status red_run(const RedPlan &plan, const Op &op) {
             // f32 Max = 1.7 waves ran at 86 % of peak).
             const bool heavy = Op::ordered || sizeof(State) > 8;
             const bool enough_waves = rc >= (int64_t)sms * 64 * 4 || bytes <= 16384;
-            // 1-byte elements (All / Any / CountTrue over bool rows): a 16 KiB row is only 8 load groups of a warp;
-            // split over a CTA every warp gets ONE group and the CTA's barriers and combine dominate (58-67 % of peak)
-            const bool small_elems = sizeof(typename Op::In) == 1 && bytes <= 32768 && rc >= warps_wanted / 2;
-            if (bytes <= 4096 || small_elems || (heavy && rc >= warps_wanted && bytes <= 65536 && enough_waves)) {
+            // (bool rows of 16 KiB — All / Any / CountTrue over [16384,16384] — run at 57-65 % of peak CTA-per-row;
+            // warp-per-row was tried for them and is worse, 35-39 %: too few warps with too long a chain each)
+            if (bytes <= 4096 || (heavy && rc >= warps_wanted && bytes <= 65536 && enough_waves)) {
                 p.parts = 1;
                 p.part_len = L;
                 int64_t ctas = (rc + kRedWarps - 1) / kRedWarps;
