@@ -235,6 +235,9 @@ struct BinParams {
     uint32_t *out_lin;                // level 1 output
     uint16_t *out_low;                // level 2 output: index inside the fine bin
     char *out_vals;
+    uint32_t *cursor;                 // [nbins]: next free slot of every bin of this level (starts as bin_start)
+    const uint32_t *coarse_start;     // level 2: [ncoarse + 1] starts of the coarse bins in the level-1 output
+    uint32_t ncoarse;
 };
 
 // Linear target element index of walked position f, or false when an index is out of range.
@@ -328,51 +331,132 @@ __global__ void __launch_bounds__(1024) scatter_scan_kernel(uint32_t *bin_start,
     if (threadIdx.x == 1023) bin_start[nbins] = part[1023];
 }
 
-// FINAL: the bins of this level are the fine bins: write the index inside the bin (u16); otherwise the full index.
+// Staged partition of one level. A tile of kTile elements is ranked by bin INSIDE shared memory and copied out bin
+// by bin, so that consecutive threads write consecutive addresses of each bin's run (whole sectors), instead of every
+// lane of a store hitting a different run (one 8-byte sector write per lane: measured 2.2 ms per level). Space in the
+// output is reserved per (tile, bin) with one global atomic on the bin's cursor.
+//   PAIRS = false (level 1): tiles walk the source through the index tensors; the digit is lin >> bin_log.
+//   PAIRS = true  (level 2): tiles walk the level-1 output INSIDE one coarse bin (they never straddle two), the digit is
+//                            the fine bin within that coarse bin (kFinePerCoarse of them).
+//   FINAL: this level's bins are the fine bins: the index inside the bin (u16) is written; otherwise the full index.
+constexpr int kTile = kBinThreads * 8;
+constexpr int kFinePerCoarseLog = 7, kFinePerCoarse = 1 << kFinePerCoarseLog;
+constexpr int kMaxRadix = 128;
+
+template <class TA>
+struct PartitionSmem {
+    uint32_t hist[kMaxRadix], scan[kMaxRadix], fill[kMaxRadix], gbase[kMaxRadix];
+    uint32_t tile_prefix[65];   // level 2: tiles before coarse bin b
+    uint32_t key[kTile];
+    uint8_t digit[kTile];
+    TA val[kTile];
+};
+
 template <bool PAIRS, bool FINAL, class TS, class TA, int NDI, int NDO>
-__global__ void __launch_bounds__(kBinThreads) scatter_partition_kernel(const __grid_constant__ BinParams p) {
-    extern __shared__ uint32_t sh_cur[];
-    const uint32_t *mine = p.cta_hist + (uint64_t)blockIdx.x * p.nbins;
-    for (uint32_t b = threadIdx.x; b < p.nbins; b += kBinThreads) sh_cur[b] = p.bin_start[b] + mine[b];
-    __syncthreads();
-    const uint64_t begin = (uint64_t)blockIdx.x * p.chunk;
-    uint64_t end = begin + p.chunk;
-    if (end > p.n) end = p.n;
-    constexpr int U = 4;
-    const uint32_t mask = (1u << p.bin_log) - 1;
-    TA *vals = reinterpret_cast<TA *>(p.out_vals);
+__global__ void __launch_bounds__(kBinThreads, 2) scatter_partition_kernel(const __grid_constant__ BinParams p) {
+    extern __shared__ __align__(16) unsigned char sh_part_raw[];
+    PartitionSmem<TA> &sm = *reinterpret_cast<PartitionSmem<TA> *>(sh_part_raw);
+    const int tid = threadIdx.x;
+    uint32_t ntiles;
+    if constexpr (PAIRS) {
+        // tiles per coarse bin from the level-1 bin starts (coarse_start has ncoarse + 1 entries)
+        if (tid == 0) {
+            uint32_t run = 0;
+            for (uint32_t b = 0; b < p.ncoarse; ++b) {
+                sm.tile_prefix[b] = run;
+                run += (p.coarse_start[b + 1] - p.coarse_start[b] + kTile - 1) / kTile;
+            }
+            sm.tile_prefix[p.ncoarse] = run;
+        }
+        __syncthreads();
+        ntiles = sm.tile_prefix[p.ncoarse];
+    } else {
+        ntiles = (p.n + kTile - 1) / kTile;
+    }
+    const uint32_t radix = PAIRS ? (uint32_t)kFinePerCoarse : p.nbins;
     const TA *in_vals = reinterpret_cast<const TA *>(p.in_vals);
-    for (uint64_t base = begin; base < end; base += (uint64_t)kBinThreads * U) {
-        uint32_t lin[U];
-        int64_t so[U];
-        bool ok[U], valid[U];
-        TA v[U];
+    TA *out_vals = reinterpret_cast<TA *>(p.out_vals);
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint32_t begin, end, bin0 = 0;
+        if constexpr (PAIRS) {
+            uint32_t cb = 0;  // coarse bin of this tile: last b with tile_prefix[b] <= tile (<= 64 entries)
+            for (uint32_t step = 32; step >= 1; step >>= 1)
+                if (cb + step < p.ncoarse && sm.tile_prefix[cb + step] <= tile) cb += step;
+            begin = p.coarse_start[cb] + (tile - sm.tile_prefix[cb]) * kTile;
+            end = begin + kTile < p.coarse_start[cb + 1] ? begin + kTile : p.coarse_start[cb + 1];
+            bin0 = cb << kFinePerCoarseLog;
+        } else {
+            begin = tile * kTile;
+            end = begin + kTile < p.n ? begin + kTile : p.n;
+        }
+        if (tid < kMaxRadix) { sm.hist[tid] = 0; sm.fill[tid] = 0; }
+        __syncthreads();
+        // 1. load the tile, count the digits
+        uint32_t lin[8];
+        TA v[8];
+        int dg[8];
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const uint64_t f = base + (uint32_t)j * kBinThreads + threadIdx.x;
-            valid[j] = true;
-            if constexpr (PAIRS) {
-                ok[j] = f < end;
-                if (ok[j]) { lin[j] = p.in_lin[f]; v[j] = in_vals[f]; }
-            } else {
-                ok[j] = f < end;
-                valid[j] = ok[j] && bin_target<NDI, NDO>(p, (uint32_t)f, so[j], lin[j]);
-                if (!valid[j]) lin[j] = 0;
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t f = begin + (uint32_t)k * kBinThreads + tid;
+            dg[k] = -1;
+            if (f < end) {
+                if constexpr (PAIRS) {
+                    lin[k] = p.in_lin[f];
+                    v[k] = in_vals[f];
+                    dg[k] = (int)((lin[k] >> p.bin_log) - bin0);
+                } else {
+                    int64_t so;
+                    if (bin_target<NDI, NDO>(p, f, so, lin[k])) {
+                        v[k] = (TA)*reinterpret_cast<const TS *>(p.gs.it_ptr + so);
+                    } else {  // out-of-range index: raise the flag, travel on as "add 0 to element 0"
+                        atomicExch(p.gs.err, 1);
+                        lin[k] = 0;
+                        v[k] = TA(0);
+                    }
+                    dg[k] = (int)(lin[k] >> p.bin_log);
+                }
+                atomicAdd(&sm.hist[dg[k]], 1u);
             }
         }
-        if constexpr (!PAIRS) {
+        __syncthreads();
+        // 2. exclusive scan of the digit counts (warp 0, 4 digits per lane) and space reservation per (tile, bin)
+        if (tid < 32) {
+            uint32_t c[4], sum = 0;
 #pragma unroll
-            for (int j = 0; j < U; ++j)
-                if (ok[j]) v[j] = valid[j] ? (TA)*reinterpret_cast<const TS *>(p.gs.it_ptr + so[j]) : TA(0);
-        }
+            for (int j = 0; j < 4; ++j) { c[j] = (uint32_t)(tid * 4 + j) < radix ? sm.hist[tid * 4 + j] : 0; sum += c[j]; }
+            uint32_t incl = sum;
 #pragma unroll
-        for (int j = 0; j < U; ++j)
-            if (ok[j]) {
-                const uint32_t pos = atomicAdd(&sh_cur[lin[j] >> p.bin_log], 1u);
-                if constexpr (FINAL) p.out_low[pos] = (uint16_t)(lin[j] & mask);
-                else p.out_lin[pos] = lin[j];
-                vals[pos] = v[j];
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+                if (tid >= off) incl += o;
             }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { sm.scan[tid * 4 + j] = run; run += c[j]; }
+        }
+        if ((uint32_t)tid < radix && sm.hist[tid] > 0) sm.gbase[tid] = atomicAdd(&p.cursor[bin0 + tid], sm.hist[tid]);
+        __syncthreads();
+        // 3. rank inside the tile, stage bin by bin
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (dg[k] >= 0) {
+                const uint32_t pos = sm.scan[dg[k]] + atomicAdd(&sm.fill[dg[k]], 1u);
+                sm.key[pos] = lin[k];
+                sm.digit[pos] = (uint8_t)dg[k];
+                sm.val[pos] = v[k];
+            }
+        __syncthreads();
+        // 4. copy out: consecutive threads -> consecutive slots of a bin's run
+        const uint32_t count = end - begin;
+        const uint32_t mask = (1u << p.bin_log) - 1;
+        for (uint32_t i = tid; i < count; i += kBinThreads) {
+            const uint32_t d = sm.digit[i];
+            const uint32_t gpos = sm.gbase[d] + (i - sm.scan[d]);
+            if constexpr (FINAL) p.out_low[gpos] = (uint16_t)(sm.key[i] & mask);
+            else p.out_lin[gpos] = sm.key[i];
+            out_vals[gpos] = sm.val[i];
+        }
+        __syncthreads();
     }
 }
 
@@ -436,7 +520,7 @@ bool dense_row_major(const dn_tensor *t) {
     return true;
 }
 
-// hist -> offsets -> scan -> partition for one level. `p` carries the level's bins, inputs and outputs.
+// hist -> offsets -> scan -> (cursors = bin starts) -> staged partition for one level.
 template <bool PAIRS, bool FINAL, class TS, class TA>
 dn_status scatter_partition_level(BinParams &p, int grid) {
     const size_t hist_smem = (size_t)p.nbins * 4;
@@ -444,8 +528,23 @@ dn_status scatter_partition_level(BinParams &p, int grid) {
                         DN_LAUNCH((scatter_hist_kernel<PAIRS, NDI, NDO>), grid, kBinThreads, hist_smem, p));
     DN_LAUNCH(scatter_offsets_kernel, (unsigned)((p.nbins + 255) / 256), 256, 0, p.cta_hist, p.bin_start, p.nbins, (uint32_t)grid);
     DN_LAUNCH(scatter_scan_kernel, 1, 1024, 0, p.bin_start, p.nbins);
+    DN_CUDA_TRY(cudaMemcpyAsync(p.cursor, p.bin_start, (size_t)p.nbins * 4, cudaMemcpyDeviceToDevice, current_stream()));
+    const int part_smem = (int)sizeof(PartitionSmem<TA>);
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
+        DN_GS_RANK_DISPATCH(p.gs.nd_it, p.gs.nd_other,
+                            cudaFuncSetAttribute(scatter_partition_kernel<PAIRS, FINAL, TS, TA, NDI, NDO>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, part_smem));
+        // (the attribute is per kernel instantiation and device; a different rank pair sets it again below)
+    }
     DN_GS_RANK_DISPATCH(p.gs.nd_it, p.gs.nd_other,
-                        DN_LAUNCH((scatter_partition_kernel<PAIRS, FINAL, TS, TA, NDI, NDO>), grid, kBinThreads, hist_smem, p));
+                        cudaFuncSetAttribute(scatter_partition_kernel<PAIRS, FINAL, TS, TA, NDI, NDO>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, part_smem));
+    const int pgrid = sm_count() * 2;
+    DN_GS_RANK_DISPATCH(p.gs.nd_it, p.gs.nd_other,
+                        DN_LAUNCH((scatter_partition_kernel<PAIRS, FINAL, TS, TA, NDI, NDO>), pgrid, kBinThreads, part_smem, p));
     return launch_status("scatter partition kernels");
 }
 
@@ -456,16 +555,16 @@ dn_status scatter_binned(const GSParams &gs, const dn_tensor *acc, int64_t nt, b
     const int esz = (int)sizeof(TA);
     const uint32_t fine_log = esz == 8 ? 13 : 14;   // 64 KiB of accumulators per CTA
     const int64_t nfine = (nt + (1ll << fine_log) - 1) >> fine_log;
-    // NOT the default yet (still slower than one warp-aggregated L2 atomic per element).
-    // DN_SCATTER_BINNED=1: always (the parity tests cover it at small sizes); =2: for large problems only (tools).
+    // NOT the default yet. DN_SCATTER_BINNED=1: always (the parity tests cover it at small
+    // sizes); =2: for large problems only (tools).
     static const int mode = [] { const char *e = getenv("DN_SCATTER_BINNED"); return e ? atoi(e) : 0; }();
     if (mode <= 0 || nfine > kMaxBins || !dense_row_major(acc) || gs.n == 0 || nt == 0) return DN_OK;
     if (mode != 1 && (gs.n < (1u << 22) || nt < (1ll << 20))) return DN_OK;
-    // coarse bins: at most 64, each a whole number of fine bins (at most 128 of them)
-    uint32_t coarse_log = fine_log;
-    while (((nt + (1ll << coarse_log) - 1) >> coarse_log) > 64) ++coarse_log;
+    // coarse bins: kFinePerCoarse fine bins each (at most 64 of them); a target of at most kMaxRadix fine bins needs
+    // one level only
+    const bool two_level = nfine > kMaxRadix;
+    const uint32_t coarse_log = fine_log + kFinePerCoarseLog;
     const int64_t ncoarse = (nt + (1ll << coarse_log) - 1) >> coarse_log;
-    const bool two_level = coarse_log > fine_log;
     BinParams p;
     p.gs = gs;
     p.n = gs.n;
@@ -476,20 +575,25 @@ dn_status scatter_binned(const GSParams &gs, const dn_tensor *acc, int64_t nt, b
     chunk = (chunk + kBinThreads * 4 - 1) / (kBinThreads * 4) * (kBinThreads * 4);
     p.chunk = chunk;
     const int grid = (int)(((uint64_t)gs.n + chunk - 1) / chunk);
-    void *s_hist = nullptr, *s_start = nullptr, *s_lin = nullptr, *s_vals1 = nullptr, *s_low = nullptr, *s_vals2 = nullptr;
+    void *s_hist = nullptr, *s_start = nullptr, *s_start1 = nullptr, *s_cursor = nullptr, *s_lin = nullptr, *s_vals1 = nullptr,
+         *s_low = nullptr, *s_vals2 = nullptr;
     dn_status st = scratch_alloc((size_t)grid * nfine * 4, &s_hist);
     if (st == DN_OK) st = scratch_alloc((size_t)(nfine + 1) * 4, &s_start);
+    if (st == DN_OK) st = scratch_alloc((size_t)(ncoarse + 1) * 4, &s_start1);
+    if (st == DN_OK) st = scratch_alloc((size_t)(nfine + 1) * 4, &s_cursor);
     if (st == DN_OK && two_level) st = scratch_alloc((size_t)gs.n * 4, &s_lin);
     if (st == DN_OK && two_level) st = scratch_alloc((size_t)gs.n * esz, &s_vals1);
     if (st == DN_OK) st = scratch_alloc((size_t)gs.n * 2, &s_low);
     if (st == DN_OK) st = scratch_alloc((size_t)gs.n * esz, &s_vals2);
     if (st == DN_OK) {
         p.cta_hist = static_cast<uint32_t *>(s_hist);
-        p.bin_start = static_cast<uint32_t *>(s_start);
+        p.cursor = static_cast<uint32_t *>(s_cursor);
         p.in_lin = nullptr;
         p.in_vals = nullptr;
         p.out_lin = static_cast<uint32_t *>(s_lin);
         p.out_low = static_cast<uint16_t *>(s_low);
+        p.coarse_start = nullptr;
+        p.ncoarse = 0;
         static std::atomic<bool> configured[64];
         int dev = 0;
         cudaGetDevice(&dev);
@@ -500,14 +604,18 @@ dn_status scatter_binned(const GSParams &gs, const dn_tensor *acc, int64_t nt, b
         if (two_level) {
             p.nbins = (uint32_t)ncoarse;
             p.bin_log = coarse_log;
+            p.bin_start = static_cast<uint32_t *>(s_start1);
             p.out_vals = static_cast<char *>(s_vals1);
             st = scatter_partition_level<false, false, TS, TA>(p, grid);
             p.in_lin = p.out_lin;
             p.in_vals = p.out_vals;
+            p.coarse_start = static_cast<const uint32_t *>(s_start1);
+            p.ncoarse = (uint32_t)ncoarse;
         }
         if (st == DN_OK) {
             p.nbins = (uint32_t)nfine;
             p.bin_log = fine_log;
+            p.bin_start = static_cast<uint32_t *>(s_start);
             p.out_vals = static_cast<char *>(s_vals2);
             st = two_level ? scatter_partition_level<true, true, TS, TA>(p, grid)
                            : scatter_partition_level<false, true, TS, TA>(p, grid);
@@ -521,6 +629,8 @@ dn_status scatter_binned(const GSParams &gs, const dn_tensor *acc, int64_t nt, b
     }
     scratch_free(s_hist);
     scratch_free(s_start);
+    scratch_free(s_start1);
+    scratch_free(s_cursor);
     scratch_free(s_lin);
     scratch_free(s_vals1);
     scratch_free(s_low);

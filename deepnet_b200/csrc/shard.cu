@@ -48,7 +48,9 @@ struct ShardRank {
     int64_t heap_used = 0;
     uint32_t epoch = 0;         // collectives issued by this (local) rank
     uint32_t scratch_uses = 0;
-    int64_t last_target = -1;   // window offset of the previous collective's target
+    int64_t last_target = -1;   // window offset of the previous collective's target (outside brackets)
+    int64_t prev_targets[8], cur_targets[8];  // targets of the previous / the current bracket
+    int nprev = 0, ncur = 0;
     int64_t *host_counts = nullptr;  // pinned, kMaxShardRanks entries: read-back of dn_shard_count_true
     bool has_pending = false;        // inside dn_shard_group_start / _end: the deferred wait + post job
     PeerSync pending_sync = {};
@@ -109,7 +111,7 @@ PeerSync make_sync(ShardGroup &g, ShardRank &me, int rank, bool with_data) {
     ps.error = reinterpret_cast<uint32_t *>(me.window + kErrorOff);
     // one rank per process: the wait half runs inside the signalling kernel (peer.cuh); several local ranks: as
     // stream memory operations, deferred to dn_shard_group_end inside a bracket
-    ps.wait_in_kernel = g.nlocal == 1 ? 1 : 0;
+    ps.wait_in_kernel = (g.nlocal == 1 && !g.grouping) ? 1 : 0;
     return ps;
 }
 
@@ -117,10 +119,30 @@ __global__ void peer_barrier_kernel(const __grid_constant__ PeerSync ps) {
     if (threadIdx.x == 0) peer_signal(ps);
 }
 
+// The wait half on its own, as a one-thread kernel (a process that drives a single rank closing a bracket).
+__global__ void peer_wait_kernel(const __grid_constant__ PeerSync ps) {
+    if (threadIdx.x != 0) return;
+    const uint64_t t0 = global_timer_ns();
+    for (int k = 0; k < ps.nflags; ++k) {
+        while ((int32_t)(ld_relaxed_sys_u32(ps.flag_local + k) - ps.epoch) < 0) {
+            if (global_timer_ns() - t0 > 20000000000ull) {
+                *ps.error = 1;
+                return;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
 // The wait half of the barrier: the stream does not proceed until every rank's flag in the LOCAL window has
-// reached `epoch` (cyclic >=). Stream memory operations: no SM is occupied while waiting.
-dn_status enqueue_wait(const PeerSync &ps) {
+// reached `epoch` (cyclic >=). Stream memory operations (no SM is occupied while waiting) when the process drives
+// several ranks; a one-thread kernel when it drives one (`spin`).
+dn_status enqueue_wait(const PeerSync &ps, bool spin = false) {
     if (ps.wait_in_kernel) return DN_OK;  // the signalling kernel has already waited
+    if (spin) {
+        DN_LAUNCH(peer_wait_kernel, 1, 32, 0, ps);
+        return launch_status("shard wait kernel");
+    }
     CUstreamBatchMemOpParams ops[kMaxShardRanks];
     memset(ops, 0, sizeof ops);
     for (int k = 0; k < ps.nflags; ++k) {
@@ -199,8 +221,11 @@ dn_status run_post(ShardRank &me, const PostJob &job);  // below, next to the fo
 // ncclGroupStart / ncclGroupEnd exist.
 dn_status complete(ShardGroup &g, ShardRank &me, const PeerSync &ps, const PostJob &job) {
     if (g.grouping) {
-        if (me.has_pending)
-            return set_error(DN_ERR_INVALID_ARG, "one collective per rank between dn_shard_group_start and dn_shard_group_end");
+        // several collectives per rank may share a bracket: flags only grow, so waiting for the LAST epoch covers the
+        // earlier ones. A collective with a post step needs its wait first and therefore has to be the last one.
+        if (me.has_pending && me.pending_job.kind != 0)
+            return set_error(DN_ERR_INVALID_ARG, "inside a bracket a reduction over the sharded axis / count exchange "
+                                                 "must be the rank's last collective");
         me.has_pending = true;
         me.pending_sync = ps;
         me.pending_job = job;
@@ -219,16 +244,29 @@ bool in_heap(const ShardGroup &g, const ShardRank &r, const char *p, int64_t nby
 // so every rank takes the same decision.
 dn_status guard_target(ShardGroup &g, ShardRank &me, int rank, const char *target) {
     const int64_t off = target - me.window;
-    if (off == me.last_target) {
-        if (g.grouping)
-            return set_error(DN_ERR_INVALID_ARG, "the same target twice in a row inside a group bracket: issue "
-                                                 "dn_shard_barrier on every rank (its own bracket) in between");
+    if (g.grouping) {
+        // a peer may be one bracket ahead: this bracket's targets must differ from each other and from the previous
+        // bracket's (they are free again from the bracket after that, or after a dn_shard_barrier)
+        for (int i = 0; i < me.ncur; ++i)
+            if (me.cur_targets[i] == off)
+                return set_error(DN_ERR_INVALID_ARG, "the same target twice inside one bracket");
+        for (int i = 0; i < me.nprev; ++i)
+            if (me.prev_targets[i] == off)
+                return set_error(DN_ERR_INVALID_ARG, "a target of the previous bracket is reused: alternate two sets of "
+                                                     "targets or issue dn_shard_barrier on every rank in between");
+        if (me.ncur < 8) me.cur_targets[me.ncur++] = off;
+        return DN_OK;
+    }
+    bool recent = off == me.last_target;
+    for (int i = 0; i < me.nprev; ++i) recent = recent || me.prev_targets[i] == off;
+    if (recent) {
         const PeerSync ps = make_sync(g, me, rank, false);
         dn_status st = launch_signal(ps);
         if (st == DN_OK) st = enqueue_wait(ps);
         if (st != DN_OK) return st;
     }
     me.last_target = off;
+    me.nprev = 0;
     return DN_OK;
 }
 
@@ -505,6 +543,7 @@ dn_status dn_shard_barrier(void *group, int32_t rank) {
     if (st != DN_OK) return st;
     RankScope scope(*me);
     me->last_target = -1;
+    me->nprev = 0;
     const PeerSync ps = make_sync(*g, *me, rank, false);
     if ((st = launch_signal(ps)) != DN_OK) return st;
     return complete(*g, *me, ps, PostJob());
@@ -526,10 +565,15 @@ dn_status dn_shard_group_end(void *group) {
     dn_status first = DN_OK;
     for (int k = 0; k < g->world; ++k) {
         ShardRank &r = g->r[k];
-        if (!r.local || !r.has_pending) continue;
+        if (!r.local) continue;
+        for (int i = 0; i < r.ncur; ++i) r.prev_targets[i] = r.cur_targets[i];
+        r.nprev = r.ncur;
+        r.ncur = 0;
+        r.last_target = -1;
+        if (!r.has_pending) continue;
         r.has_pending = false;
         RankScope scope(r);
-        dn_status st = enqueue_wait(r.pending_sync);
+        dn_status st = enqueue_wait(r.pending_sync, g->nlocal == 1);
         if (st == DN_OK) st = run_post(r, r.pending_job);
         if (st != DN_OK && first == DN_OK) first = st;
     }

@@ -101,6 +101,16 @@ class ShardGroup:
         else:
             yield
 
+    @contextmanager
+    def batch(self):
+        """A bracket in any process model: the collectives issued inside launch back to back and share ONE wait at
+        the end (dn_shard_group_end). Targets inside must be distinct."""
+        self.api.call("shard_group_start", self._g)
+        try:
+            yield
+        finally:
+            self.api.call("shard_group_end", self._g)
+
     def barrier(self) -> None:
         with self.bracket():
             for r in self.ranks:

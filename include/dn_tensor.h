@@ -319,13 +319,17 @@ dn_status dn_shard_heap_alloc(void *group, int32_t rank, int64_t nbytes, void **
 dn_status dn_shard_heap_reset(void *group, int32_t rank);
 /* Flag barrier over peer memory on the ranks' streams (one tiny kernel per rank). */
 dn_status dn_shard_barrier(void *group, int32_t rank);
-/* ONE thread driving several ranks brackets every collective (as with ncclGroupStart / ncclGroupEnd):
- *     dn_shard_group_start(g);  for each local rank r: dn_shard_<op>(g, r, ...);  dn_shard_group_end(g);
- * Inside the bracket a call launches the rank's kernel (stores + signal) at once and defers the wait half of the
- * barrier — and whatever needs every rank's contribution — to dn_shard_group_end, when every local rank has issued:
- * a stream already waiting for a peer whose kernel the same thread has yet to launch would turn any blocking call on
- * the way there into a deadlock. One collective per rank per bracket. Not needed (and not wanted) with one thread or
- * one process per rank: there every call completes its own wait. */
+/* Brackets (as ncclGroupStart / ncclGroupEnd). Inside a bracket a collective launches its kernel (stores + signal)
+ * at once and DEFERS the wait half of the barrier — and whatever needs every rank's contribution — to
+ * dn_shard_group_end, which enqueues ONE wait per rank for the rank's last collective (flags only grow).
+ *   - ONE thread driving several ranks MUST bracket:  start;  for each local rank r: dn_shard_<op>(g, r, ...);  end.
+ *     A stream already waiting for a peer whose kernel the same thread has yet to launch would turn any blocking call
+ *     on the way there into a deadlock.
+ *   - Any caller MAY bracket several collectives per rank (e.g. ArgMax and Max of the same logits): their waits
+ *     coalesce into one, and the kernels run back to back. Results are ordered on the rank's stream after
+ *     dn_shard_group_end; targets inside one bracket must be distinct; a reduction over the sharded axis or a count
+ *     exchange (they need their wait first) must be the rank's last collective of the bracket.
+ * Outside brackets every call completes its own wait. */
 dn_status dn_shard_group_start(void *group);
 dn_status dn_shard_group_end(void *group);
 

@@ -137,6 +137,17 @@ def run(grp: ShardGroup, set_device) -> list:
             fused_v2[r], fused_i2[r] = grp.minmax_arg(r, False, loc[r]["f"], R, loc[r]["beg"])
     results.append(("fused Min", fused_v2, hf.minAxis(1).toNumpy(), 0.0))
     results.append(("fused ArgMin", fused_i2, hf.argMinAxis(1).toNumpy(), 0.0))
+    # several collectives per rank in ONE bracket (one wait at the end): ArgMax, Max and a sharded-axis Sum (last)
+    bi, bm, bs = {}, {}, {}
+    with grp.batch():
+        for r in grp.ranks:
+            set_device(r)
+            bi[r] = grp.reduce_axis(r, "ArgMaxLastAxis", loc[r]["f"], 1, R, loc[r]["beg"])
+            bm[r] = grp.reduce_axis(r, "MaxLastAxis", loc[r]["f"], 1, R, loc[r]["beg"])
+            bs[r] = grp.reduce_axis(r, "SumLastAxis", loc[r]["i"], 0, R, loc[r]["beg"])
+    results.append(("bracket of three: ArgMax", bi, hf.argMaxAxis(1).toNumpy(), 0.0))
+    results.append(("bracket of three: Max", bm, hf.maxAxis(1).toNumpy(), 0.0))
+    results.append(("bracket of three: Sum over the sharded axis", bs, hi.sumAxis(0).toNumpy(), 0.0))
     # ordered compaction across the shards
     begs = {r: loc[r]["beg"] for r in grp.ranks}
     results.append(("trueIdx", grp.true_indices({r: loc[r]["b"] for r in grp.ranks}, begs), hb.trueIdx().toNumpy(), 0.0))
