@@ -353,3 +353,17 @@ def test_tf32_batched_one_launch(cuda_dev, tf32_mode):
     cc = ca @ cbt.swapDim(2, 3)
     hc = ha @ hbt.swapDim(2, 3)
     check_mm(hc[1, 1], cc[1, 1], a[1, 1], bt[1, 1].T, dtypes.DN_F32, "transposed right operand")
+
+
+def test_one_cta_kernel_stays_covered():
+    """Large tf32 products now take the CTA-pair kernel; DN_GEMM_2CTA=0 (test hook, read once per process, hence the child
+    process) sends the tf32 cases of this file through the one-CTA 128 x 256 kernel again."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DN_GEMM_2CTA") == "0":
+        pytest.skip("already running under the hook")
+    env = dict(os.environ, DN_GEMM_2CTA="0")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-k", "tf32 and not batched", "-q", "-m", "gpu", "-x"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
