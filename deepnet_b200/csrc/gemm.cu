@@ -392,18 +392,23 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
     m_blk = m_first + (in_group - n_blk * rows);
 }
 
+template <bool SPLIT = false>
 struct GemmCfg2 {
-    static constexpr int kStageBytes = (kBM + kBN2 / 2) * kBK * 4;  // 32 KiB per CTA
-    static constexpr int kStages = 6;
+    static constexpr int kHalfBytes = (kBM + kBN2 / 2) * kBK * 4;   // 32 KiB per CTA: its rows of A + its half of B
+    static constexpr int kStageBytes = kHalfBytes * (SPLIT ? 2 : 1);  // 3xTF32: plus the low-order halves
+    static constexpr int kStages = SPLIT ? 3 : 6;
     static constexpr int kTmemCols = 2 * kBN2;
     static constexpr int kEpiBytes = 4 * 32 * 33 * 4;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiBytes;
 };
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool SPLIT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-    gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
-    using Cfg = GemmCfg2;
+    gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo,
+                          const GemmParams p) {
+    static_assert(!SPLIT || (!A_MN && !B_MN), "split operands are always K-major scratch");
+    using Cfg = GemmCfg2<SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -470,6 +475,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                     } else {
                         tma_load_3d_2sm(sb, &map_b, &full[stage], kb * kBK, n0, bb);
                     }
+                    if constexpr (SPLIT) {
+                        tma_load_3d_2sm(sa + Cfg::kHalfBytes, &map_a_lo, &full[stage], kb * kBK, m0, ba);
+                        tma_load_3d_2sm(sb + Cfg::kHalfBytes, &map_b_lo, &full[stage], kb * kBK, n0, bb);
+                    }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -494,9 +503,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                     const uint64_t da = A_MN ? make_mnmajor_sw128_desc(sa) : make_kmajor_sw128_desc(sa);
                     const uint64_t db = B_MN ? make_mnmajor_sw128_desc(sb) : make_kmajor_sw128_desc(sb);
                     constexpr uint64_t stepA = A_MN ? (1024 >> 4) : (32 >> 4), stepB = B_MN ? (1024 >> 4) : (32 >> 4);
+                    if constexpr (SPLIT) {  // 3xTF32: small terms first
+                        const uint64_t da_lo = make_kmajor_sw128_desc(sa + Cfg::kHalfBytes);
+                        const uint64_t db_lo = make_kmajor_sw128_desc(sb + Cfg::kHalfBytes);
 #pragma unroll
-                    for (int k = 0; k < kBK / 8; ++k)
-                        umma_tf32_2sm(tmem_c, da + (uint64_t)k * stepA, db + (uint64_t)k * stepB, idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < kBK / 8; ++k) {
+                            umma_tf32_2sm(tmem_c, da_lo + (uint64_t)k * stepA, db + (uint64_t)k * stepB, idesc, (kb | k) ? 1u : 0u);
+                            umma_tf32_2sm(tmem_c, da + (uint64_t)k * stepA, db_lo + (uint64_t)k * stepB, idesc, 1u);
+                            umma_tf32_2sm(tmem_c, da + (uint64_t)k * stepA, db + (uint64_t)k * stepB, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kBK / 8; ++k)
+                            umma_tf32_2sm(tmem_c, da + (uint64_t)k * stepA, db + (uint64_t)k * stepB, idesc, (kb | k) ? 1u : 0u);
+                    }
                     umma_commit_2sm(&empty[stage]);
                     if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc]);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -673,19 +693,21 @@ dn_status launch_tf32(const CUtensorMap &ma, const CUtensorMap &mb, const CUtens
     return launch_status("tcgen05 GEMM kernel");
 }
 
-template <bool A_MN, bool B_MN>
-dn_status launch_tf32_2cta(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &p) {
+template <bool A_MN, bool B_MN, bool SPLIT = false>
+dn_status launch_tf32_2cta(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma_lo, const CUtensorMap &mb_lo,
+                           const GemmParams &p) {
+    using Cfg = GemmCfg2<SPLIT>;
     static std::atomic<bool> configured[64];
     int dev = 0;
     DN_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        DN_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32_2cta_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg2::kSmemBytes));
+        DN_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32_2cta_kernel<A_MN, B_MN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes));
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n * p.nbatch;
     const int pairs = tiles < sm_count() / 2 ? (int)tiles : sm_count() / 2;
-    DN_LAUNCH((gemm_tf32_2cta_kernel<A_MN, B_MN>), 2 * pairs, kGemmThreads, GemmCfg2::kSmemBytes, ma, mb, p);
+    DN_LAUNCH((gemm_tf32_2cta_kernel<A_MN, B_MN, SPLIT>), 2 * pairs, kGemmThreads, Cfg::kSmemBytes, ma, mb, ma_lo, mb_lo, p);
     return launch_status("tcgen05 2-CTA GEMM kernel");
 }
 
@@ -744,8 +766,8 @@ dn_status gemm_f32_tf32(float *c, int64_t cm, int64_t cn, const float *a, int64_
             st = b_mn ? make_map3(&mb, B.ptr, K, B.rows, B.ks, kBK, true, nb, b_bs)
                       : make_map3(&mb, B.ptr, B.rows, K, B.rs, kBN2 / 2, false, nb, b_bs);
         if (st == DN_OK) {
-            if (a_mn) st = b_mn ? launch_tf32_2cta<true, true>(ma, mb, p) : launch_tf32_2cta<true, false>(ma, mb, p);
-            else st = b_mn ? launch_tf32_2cta<false, true>(ma, mb, p) : launch_tf32_2cta<false, false>(ma, mb, p);
+            if (a_mn) st = b_mn ? launch_tf32_2cta<true, true>(ma, mb, ma, mb, p) : launch_tf32_2cta<true, false>(ma, mb, ma, mb, p);
+            else st = b_mn ? launch_tf32_2cta<false, true>(ma, mb, ma, mb, p) : launch_tf32_2cta<false, false>(ma, mb, ma, mb, p);
         }
         scratch_free(sa);
         scratch_free(sb);
@@ -950,6 +972,15 @@ dn_status gemm_f32_split(float *c, int64_t cm, int64_t cn, const float *a, int64
     GemmParams p;
     p.c = c; p.ldc_m = cm; p.ldc_n = cn;
     p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K;
+    if (st == DN_OK && tf32_pair_eligible(M, N)) {  // CTA pairs, 256 x 256 tiles, three 64 KiB stages
+        p.tiles_m = (int32_t)((M + 2 * kBM - 1) / (2 * kBM));
+        p.tiles_n = (int32_t)((N + kBN2 - 1) / kBN2);
+        st = make_map3(&ma, ahi, M, K, pa, kBM, false, 1, 0);
+        if (st == DN_OK) st = make_map3(&mal, alo, M, K, pa, kBM, false, 1, 0);
+        if (st == DN_OK) st = make_map3(&mb, bhi, N, K, pb, kBN2 / 2, false, 1, 0);
+        if (st == DN_OK) st = make_map3(&mbl, blo, N, K, pb, kBN2 / 2, false, 1, 0);
+        if (st == DN_OK) st = launch_tf32_2cta<false, false, true>(ma, mb, mal, mbl, p);
+    } else {
     const int BN = N <= 32 ? 32 : 128;
     p.tiles_m = (int32_t)((M + kBM - 1) / kBM);
     p.tiles_n = (int32_t)((N + BN - 1) / BN);
@@ -960,6 +991,7 @@ dn_status gemm_f32_split(float *c, int64_t cm, int64_t cn, const float *a, int64
     if (st == DN_OK)
         st = BN == 32 ? launch_tf32<32, false, false, true>(ma, mb, mal, mbl, p)
                       : launch_tf32<128, false, false, true>(ma, mb, mal, mbl, p);
+    }
     // an operand held an infinity or a NaN: the exact kernel recomputes the product (its launch returns at once otherwise)
     if (st == DN_OK)
         st = gemm_simt<float>(c, cm, cn, a, am, ak, b, bk, bn, M, N, K, 0, nullptr, nullptr, nullptr, nullptr, nonfinite);
