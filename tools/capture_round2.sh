@@ -7,8 +7,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 bash tools/ncu_capture.sh r02_ew_add_contig256_f64 "ew_kernel" 0 python tools/perf_sweep.py --filter "C2 double add contiguous" --reps 2
 bash tools/ncu_capture.sh r02_fused_spec_tanh_grad "ew_kernel" 2 python tools/perf_sweep.py --filter "FUSED f32 dh" --reps 2
 bash tools/ncu_capture.sh r02_reduce_max_argmax_c3 "reduce_rows_kernel" 2 python tools/perf_sweep.py --filter "C3 f32 max+argmax" --reps 2
-bash tools/ncu_capture.sh r02_gemm_tf32_8192x4096x4096 "gemm_tf32_kernel" 2 python tools/gemm_bench.py tf32 fwd2
-bash tools/ncu_capture.sh r02_gemm_3xtf32_8192x4096x4096 "gemm_tf32_kernel" 2 python tools/gemm_bench.py fp32 fwd2
+bash tools/ncu_capture.sh r02_gemm_tf32_2cta_8192x4096x4096 "gemm_tf32_2cta_kernel" 2 python tools/gemm_bench.py tf32 fwd2
+bash tools/ncu_capture.sh r02_gemm_3xtf32_2cta_8192x4096x4096 "gemm_tf32_2cta_kernel" 2 python tools/gemm_bench.py fp32 fwd2
 bash tools/ncu_capture.sh r02_scatter_partition "scatter_partition_kernel" 2 python tools/perf_sweep.py --filter "C4 i64 scatter random" --reps 2
 bash tools/ncu_capture.sh r02_scatter_accumulate "scatter_accumulate_kernel" 1 python tools/perf_sweep.py --filter "C4 i64 scatter random" --reps 2
 rm -f gpurun_out/r02_*.source.csv
