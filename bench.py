@@ -48,7 +48,7 @@ SIDE = 16384  # 2^28 elements per tensor
 # `ncu --set full` captures (file named per entry); None for kernels without a capture.
 NCU_TRAFFIC = {
     "ew_kernel<BinaryF<float,ADD>,VEC=8> (256-bit vector kernel)": (2.147553e9 + 1.041274e9, "profiles/r01b_ew_add_contig256.raw.csv"),
-    "ew_kernel<BinaryF<double,ADD>,VEC=4> (256-bit vector kernel)": (4.294980e9 + 2.118896e9, "profiles/r01c_ew_add_contig256_f64.raw.csv"),
+    "ew_kernel<BinaryF<double,ADD>,VEC=4> (256-bit vector kernel)": (4.295071e9 + 2.117457e9, "profiles/r02_ew_add_contig256_f64.raw.csv"),
     "ew_xpose_kernel<BinaryF<float,ADD>> (register transpose)": (2.147507e9 + 1.039083e9, "profiles/r01_ew_xpose_addT.raw.csv"),
     "ew_xpose_kernel<BinaryF<double,ADD>> (register transpose)": (4.295036e9 + 2.110988e9, "profiles/r01_ew_xpose_f64_addT.raw.csv"),
 }

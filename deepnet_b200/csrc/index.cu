@@ -1188,6 +1188,7 @@ __global__ void __launch_bounds__(kIdxThreads) separable_kernel(const __grid_con
     for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < p.n; f += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t rem = (uint32_t)f;
         int64_t doff = 0, foff = 0;
+        bool selected = true;   // false: a dense position beyond the number of selected elements (list entry -1)
 #pragma unroll
         for (int k = 0; k < DN_MAX_DIMS; ++k) {
             if (k >= p.nd) break;
@@ -1196,9 +1197,11 @@ __global__ void __launch_bounds__(kIdxThreads) separable_kernel(const __grid_con
             else { q = p.ddiv[k].div(rem); x = rem - q * p.dshape[k]; }
             doff += (int64_t)x * p.dstride[k];
             const int64_t fx = p.sel[k] ? p.sel[k][x] : (int64_t)x;
+            selected = selected && fx >= 0;
             foff += fx * p.fstride[k];
             rem = q;
         }
+        if (!selected) continue;
         if (IsGet) *reinterpret_cast<B *>(p.dense + doff) = *reinterpret_cast<const B *>(p.full + foff);
         else *reinterpret_cast<B *>(p.full + foff) = *reinterpret_cast<const B *>(p.dense + doff);
     }
@@ -1238,8 +1241,13 @@ dn_status masked_general(const dn_tensor *dense, const dn_tensor *full, const dn
     void *scratch = nullptr;
     dn_status st = scratch_alloc((size_t)(total + 1) * sizeof(int64_t), &scratch);
     if (st != DN_OK) return st;
-    // zero the lists so that a target larger than the number of selected elements reads index 0, never garbage
-    cudaMemsetAsync(scratch, 0, (size_t)(total + 1) * sizeof(int64_t), current_stream());
+    // the lists start as -1: a dense side larger than the number of selected elements leaves its surplus positions
+    // untouched (the host backend walks the selected elements only, ScalarOps.fs:667-707)
+    const cudaError_t me = cudaMemsetAsync(scratch, 0xFF, (size_t)(total + 1) * sizeof(int64_t), current_stream());
+    if (me != cudaSuccess) {
+        scratch_free(scratch);
+        return cuda_error(me, what);
+    }
     SepParams p;
     int64_t *cursor = reinterpret_cast<int64_t *>(scratch);
     const int sz = dtype_size(full->dtype);

@@ -342,6 +342,22 @@ __device__ __forceinline__ void warp_arg_combine32(T &val, int &ridx) {
     }
 }
 
+// The arg fold of an op (ArgOp itself, or the arg half of the fused value+index op): extremum of two candidates
+// and the fold's start value.
+template <class Op> struct ArgPick {
+    using T = typename Op::In;
+    __device__ static T pick(T a, T b) { return a; }
+    __device__ static T lowest() { return T(); }
+};
+template <class T, bool IsMax> struct ArgPick<ArgOp<T, IsMax>> {
+    __device__ static T pick(T a, T b) { return ArgOp<T, IsMax>::pick(a, b); }
+    __device__ static T lowest() { return IsMax ? Limits<T>::lowest() : Limits<T>::max(); }
+};
+template <class T, bool IsMax> struct ArgPick<MinMaxArgOp<T, IsMax>> {
+    __device__ static T pick(T a, T b) { return ArgOp<T, IsMax>::pick(a, b); }
+    __device__ static T lowest() { return IsMax ? Limits<T>::lowest() : Limits<T>::max(); }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // rows family
 // ---------------------------------------------------------------------------------------------------------------
@@ -362,32 +378,45 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
     int ridx = -1;          // arg ops only: lane-local best index relative to `begin`
     const T *p = reinterpret_cast<const T *>(row);
 
-    // fold one round: this lane holds n (0..VEC) consecutive elements starting at index i0
-    auto round = [&](const T *v, int n, int64_t i0) {
+    // fold one round: this lane holds n (0..VEC) consecutive elements starting at index i0; FULL: n == VEC, known at
+    // compile time (no per-element predicates — every round but the head and the last one of a part).
+    // The arg folds work per VECTOR: the vector's extremum (NaNs dropped by FMNMX, as the strict compare drops them)
+    // is compared with the lane's best and the lane remembers where the winning VECTOR starts — VEC-1 min/max plus
+    // one compare and two selects per vector instead of a compare and two selects per element; which element of the
+    // winning vector it was is settled once per part, after the warp-wide combine (resolve_arg below).
+    auto round = [&](auto full_tag, const T *v, int n, int64_t i0) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        auto vec_extremum = [&]() {
+            using A = ArgPick<Op>;
+            T m = FULL ? v[0] : A::lowest();
+#pragma unroll
+            for (int j = FULL ? 1 : 0; j < VEC; ++j)
+                if (FULL || j < n) m = A::pick(m, v[j]);
+            return m;
+        };
         if constexpr (Op::ordered) {
             // cheap NaN probe: the sum of the lane's elements is NaN iff one of them is (or +inf meets -inf, a
             // false positive that the exact slow path below resolves)
             T probe = T(0);
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
-                if (j < n) probe += v[j];
+                if (FULL || j < n) probe += v[j];
+            T m = T(0);
             if constexpr (IsFusedArgOp<Op>::value) {  // the arg fold: NaNs never win (strict compare)
-                const int r0 = (int)(i0 - begin);
-#pragma unroll
-                for (int j = 0; j < VEC; ++j)
-                    if (j < n && Op::better(v[j], st.aval)) {
-                        st.aval = v[j];
-                        ridx = r0 + j;
-                    }
+                m = vec_extremum();
+                if (Op::better(m, st.aval)) {
+                    st.aval = m;
+                    ridx = (int)(i0 - begin);
+                }
             }
             if (__any_sync(kFull, probe != probe)) {  // rare
                 int64_t my_nan = -1;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
-                    if (j < n && v[j] != v[j]) my_nan = i0 + j;
+                    if ((FULL || j < n) && v[j] != v[j]) my_nan = i0 + j;
 #pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) {
-                    const int64_t o = __shfl_xor_sync(kFull, my_nan, m);
+                for (int m2 = 16; m2 >= 1; m2 >>= 1) {
+                    const int64_t o = __shfl_xor_sync(kFull, my_nan, m2);
                     my_nan = o > my_nan ? o : my_nan;
                 }
                 if (my_nan >= 0) {  // a real NaN in this round resets every lane
@@ -396,36 +425,52 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
                 }
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
-                    if (j < n && i0 + j > last_nan) st.val = Op::better(st.val, v[j]) ? st.val : v[j];
+                    if ((FULL || j < n) && i0 + j > last_nan) st.val = Op::better(st.val, v[j]) ? st.val : v[j];
             } else {
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
-                    if (j < n) st.val = Op::pick(st.val, v[j]);
+                    if (FULL || j < n) st.val = Op::pick(st.val, v[j]);
             }
         } else if constexpr (IsArgOp<Op>::value) {
-            // (value, index) pairs: the lane tracks a 32-bit index relative to `begin` (one select instead of a
-            // 64-bit pair per element); it is widened once at the end of the part
-            // (testing the vector's extremum first and searching only on a hit was tried: the branch costs more than the
-            // selects it saves — C3 ArgMax 6.42 -> 5.98 TB/s)
-            const int r0 = (int)(i0 - begin);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j)
-                if (j < n && Op::better(v[j], st.val)) {
-                    st.val = v[j];
-                    ridx = r0 + j;
-                }
+            // (testing the vector's extremum first and searching the vector only on a hit was tried: the branch costs
+            // more than the selects it saves — C3 ArgMax 6.42 -> 5.98 TB/s; the deferred search has no branch)
+            const T m = vec_extremum();
+            if (Op::better(m, st.val)) {
+                st.val = m;
+                ridx = (int)(i0 - begin);
+            }
         } else {
             if constexpr (HasPacked16<Op>::value) {
-                if (n == VEC) {  // v is a 16-byte aligned Pack
+                if constexpr (FULL) {  // v is a 16-byte aligned Pack
+                    Op::packed16(st, reinterpret_cast<const uint32_t *>(v));
+                    return;
+                } else if (n == VEC) {
                     Op::packed16(st, reinterpret_cast<const uint32_t *>(v));
                     return;
                 }
             }
+            if constexpr (!(FULL && HasPacked16<Op>::value)) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j)
-                if (j < n) op_step(op, st, v[j], i0 + j);
+                for (int j = 0; j < VEC; ++j)
+                    if (FULL || j < n) op_step(op, st, v[j], i0 + j);
+            }
         }
     };
+    // arg folds: `ridx` is where the winning vector starts (relative to `begin`); the element is the first one of
+    // that vector equal to the winning value (a NaN equals nothing; elements past the vector belong to later
+    // vectors and are only reached if nothing before them matched, which cannot happen). Uniform across the warp.
+    auto resolve_arg = [&](T best, int r) -> int64_t {
+        if (r < 0) return (int64_t)DN_NOT_FOUND;
+        int first = 0;
+#pragma unroll
+        for (int j = VEC - 1; j >= 0; --j) {
+            const int64_t e = begin + r + j;
+            if (e < end && p[e] == best) first = j;
+        }
+        return begin + r + first;
+    };
+    const std::true_type kFullRound{};
+    const std::false_type kPartRound{};
 
     int64_t i = begin;
     if (i < end) {
@@ -436,7 +481,7 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
             T v[VEC];
             const bool on = lane < head;
             if (on) v[0] = p[i + lane];
-            round(v, on ? 1 : 0, i + lane);
+            round(kPartRound, v, on ? 1 : 0, i + lane);
             i += head;
         }
         // groups of UNR rounds; only the last group of a part can be partial (per-lane predicates, scalar loads for
@@ -463,12 +508,19 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
                     }
                 }
             }
+            if (rem == ROUND * UNR) {
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int off = u * ROUND + lane * VEC;
-                if (u * ROUND < rem) {  // warp-uniform
-                    const int left = rem - off;
-                    round(buf[u].v, left >= VEC ? VEC : (left > 0 ? left : 0), i + off);
+                for (int u = 0; u < UNR; ++u) round(kFullRound, buf[u].v, VEC, i + u * ROUND + lane * VEC);
+            } else {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int off = u * ROUND + lane * VEC;
+                    if ((u + 1) * ROUND <= rem) {  // warp-uniform: a whole round
+                        round(kFullRound, buf[u].v, VEC, i + off);
+                    } else if (u * ROUND < rem) {  // warp-uniform: the part's last, ragged round
+                        const int left = rem - off;
+                        round(kPartRound, buf[u].v, left >= VEC ? VEC : (left > 0 ? left : 0), i + off);
+                    }
                 }
             }
         }
@@ -485,7 +537,7 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
             T av = st.aval;
             warp_arg_combine32<T, IsMaxOp<Op>::value>(av, ridx);
             out.aval = av;
-            out.idx = ridx >= 0 ? begin + ridx : (int64_t)DN_NOT_FOUND;
+            out.idx = resolve_arg(av, ridx);
         }
         out.flags = (end > begin ? 2 : 0) | (last_nan >= 0 ? 1 : 0);
         out.val = v;
@@ -494,7 +546,7 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
     } else {
         if constexpr (IsArgOp<Op>::value) {
             warp_arg_combine32<T, IsMaxOp<Op>::value>(st.val, ridx);
-            st.idx = ridx >= 0 ? begin + ridx : (int64_t)DN_NOT_FOUND;
+            st.idx = resolve_arg(st.val, ridx);
             return st;
         } else {
             return warp_combine_unordered<Op>(st);
@@ -507,7 +559,7 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
 // for a fifth CTA and serialises the loads — measured 5-7 % slower on C3). Sub-word types and the fused
 // value+index fold need more and get no hint.
 template <class Op> struct RowsMinBlocks { static constexpr int value = sizeof(typename Op::In) >= 4 ? 4 : 1; };
-template <class T, bool IsMax> struct RowsMinBlocks<MinMaxArgOp<T, IsMax>> { static constexpr int value = 3; };
+template <class T, bool IsMax> struct RowsMinBlocks<MinMaxArgOp<T, IsMax>> { static constexpr int value = 4; };
 
 // parts == 1: warp per row.  parts == 8*S: one CTA per (row, s); its 8 warps take consecutive parts.
 template <class Op>

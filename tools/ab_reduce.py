@@ -40,6 +40,15 @@ nb = 262144 * 1000 * 4
 out["C3 argmax"] = nb / timed(lambda: oi._fill_axis("ArgMaxLastAxis", 1, lg, True)) / 1e6
 out["C3 max"] = nb / timed(lambda: om.FillMaxAxis(1, lg)) / 1e6
 out["C3 sum"] = nb / timed(lambda: om.FillSumAxis(1, lg)) / 1e6
+if hasattr(_lib, "dn_shard_minmax_arg_last_axis"):
+    _d = lambda t: t.Backend._d(t)
+    out["C3 max+argmax one pass"] = nb / timed(lambda: dev.api.call("shard_minmax_arg_last_axis", None, 0, 1, _d(om), _d(oi), 0, _d(lg))) / 1e6
+td = torch.rand(131072, 1000, device="cuda", dtype=torch.float64) * 100 - 50
+ld = w(td, dtypes.DN_F64); oid = Tensor.empty((131072,), dtypes.DN_I64, dev)
+out["f64 131072x1000 argmax"] = 131072 * 8000 / timed(lambda: oid._fill_axis("ArgMaxLastAxis", 1, ld, True)) / 1e6
+ti8 = torch.randint(-100, 100, (262144, 1000), device="cuda", dtype=torch.int8)
+l8 = w(ti8, dtypes.DN_I8)
+out["i8 262144x1000 argmax"] = 262144 * 1000 / timed(lambda: oi._fill_axis("ArgMaxLastAxis", 1, l8, True)) / 1e6
 t2 = torch.rand(16384, 16384, device="cuda") * 100 - 50
 a2 = w(t2, dtypes.DN_F32); o2 = Tensor.empty((16384,), dtypes.DN_F32, dev); o2i = Tensor.empty((16384,), dtypes.DN_I64, dev)
 nb2 = 16384 * 16384 * 4
@@ -51,7 +60,8 @@ print(json.dumps(out))
 '''
 
 if __name__ == "__main__":
-    libs = [os.path.abspath(p) for p in sys.argv[1:]]
+    libs = [os.path.abspath(p) for p in sys.argv[1:]] or [os.path.join(ROOT, "build/ab/libdeepnet_b200_r01.so"),
+                                                          os.path.join(ROOT, "deepnet_b200/lib/libdeepnet_b200.so")]
     res = {p: [] for p in libs}
     for _ in range(3):
         for p in libs:
@@ -61,7 +71,12 @@ if __name__ == "__main__":
                 print(p, "FAILED", out.stderr[-1500:])
                 continue
             res[p].append(json.loads(out.stdout.strip().splitlines()[-1]))
-    keys = list(next(iter(res.values()))[0].keys()) if all(res.values()) else []
+    keys = []
+    for p in libs:
+        for k in (res[p][0] if res[p] else {}):
+            if k not in keys:
+                keys.append(k)
     print(f"{'GB/s (median of rounds)':28s}" + "".join(f"{os.path.basename(p)[:26]:>28s}" for p in libs))
     for k in keys:
-        print(f"{k:28s}" + "".join(f"{sorted(r[k] for r in res[p])[len(res[p]) // 2]:28.1f}" for p in libs))
+        med = lambda p: sorted(r[k] for r in res[p])[len(res[p]) // 2] if res[p] and k in res[p][0] else float("nan")
+        print(f"{k:28s}" + "".join(f"{med(p):28.1f}" for p in libs))
