@@ -373,6 +373,7 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int ROUND = 32 * VEC;
     constexpr int UNR = 4;
+    constexpr bool kVecArg = sizeof(T) >= 4;  // arg folds per vector (below)
     State st = Op::identity();
     int64_t last_nan = -1;  // ordered ops only: index of the last NaN seen by the WARP (uniform)
     int ridx = -1;          // arg ops only: lane-local best index relative to `begin`
@@ -434,10 +435,21 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
         } else if constexpr (IsArgOp<Op>::value) {
             // (testing the vector's extremum first and searching the vector only on a hit was tried: the branch costs
             // more than the selects it saves — C3 ArgMax 6.42 -> 5.98 TB/s; the deferred search has no branch)
-            const T m = vec_extremum();
-            if (Op::better(m, st.val)) {
-                st.val = m;
-                ridx = (int)(i0 - begin);
+            if constexpr (kVecArg) {
+                const T m = vec_extremum();
+                if (Op::better(m, st.val)) {
+                    st.val = m;
+                    ridx = (int)(i0 - begin);
+                }
+            } else {  // sub-word elements: per element (the byte extraction dominates; the deferred search would add
+                      // VEC scalar loads per part — int8 rows of 1000: 394 GB/s this way, 317 the other)
+                const int r0 = (int)(i0 - begin);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    if ((FULL || j < n) && Op::better(v[j], st.val)) {
+                        st.val = v[j];
+                        ridx = r0 + j;
+                    }
             }
         } else {
             if constexpr (HasPacked16<Op>::value) {
@@ -461,6 +473,7 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
     // vectors and are only reached if nothing before them matched, which cannot happen). Uniform across the warp.
     auto resolve_arg = [&](T best, int r) -> int64_t {
         if (r < 0) return (int64_t)DN_NOT_FOUND;
+        if constexpr (!kVecArg) return begin + r;
         int first = 0;
 #pragma unroll
         for (int j = VEC - 1; j >= 0; --j) {
@@ -556,8 +569,9 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
 
 // Register target of the rows kernel: the folds over 4- and 8-byte elements need <= 64 registers and run best at
 // exactly that (4 CTAs per SM: the loads of a group stay in flight; left alone ptxas squeezes them to 48 registers
-// for a fifth CTA and serialises the loads — measured 5-7 % slower on C3). Sub-word types and the fused
-// value+index fold need more and get no hint.
+// for a fifth CTA and serialises the loads — measured 5-7 % slower on C3). Sub-word types need more and get no
+// hint; the fused value+index fold fits with 12 bytes of spill and is 24 % faster for it (C3 Max+ArgMax in one pass:
+// 4.56 -> 5.67 TB/s, same box, `profiles/r02w_ab_reduce.txt`).
 template <class Op> struct RowsMinBlocks { static constexpr int value = sizeof(typename Op::In) >= 4 ? 4 : 1; };
 template <class T, bool IsMax> struct RowsMinBlocks<MinMaxArgOp<T, IsMax>> { static constexpr int value = 4; };
 

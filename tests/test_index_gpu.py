@@ -179,6 +179,32 @@ def test_masked_per_dimension(cuda_dev, dtype):
     assert_same(hT.M(hmT), cT.M(cmT), dtype, what="MaskedGet permuted view")
 
 
+def test_masked_per_dimension_surplus_positions_stay_untouched(cuda_dev):
+    """A dense side LARGER than the number of selected elements along a masked dimension (the backend call allows
+    it; the frontend sizes it exactly): the host walks the selected elements only (ScalarOps.fs:667-707), so the
+    surplus positions of a MaskedGet target keep their contents and the surplus values of a MaskedSet are not
+    stored anywhere — in particular not at index 0 (round-1 review)."""
+    rng = np.random.default_rng(41)
+    arr = rng.integers(1, 1000, size=(9, 12), dtype=np.int64)
+    m0 = np.array([0, 1, 1, 0, 0, 1, 0, 0, 0], dtype=bool)           # 3 rows selected
+    m1 = rng.uniform(0, 1, size=12) < 0.5
+    n1 = int(m1.sum())
+    src, c0, c1 = CudaTensor.ofNumpy(arr), CudaTensor.ofNumpy(m0), CudaTensor.ofNumpy(m1)
+    # MaskedGet into a target with 5 rows (2 surplus) and n1 + 1 columns (1 surplus)
+    trg = CudaTensor.ofNumpy(np.full((5, n1 + 1), -7, dtype=np.int64))
+    src.Backend.MaskedGet(trg, src, [c0, c1])
+    want = np.full((5, n1 + 1), -7, dtype=np.int64)
+    want[:3, :n1] = arr[m0][:, m1]
+    np.testing.assert_array_equal(trg.toNumpy(), want)
+    # MaskedSet from values with surplus rows / columns: only the selected cells change
+    vals = rng.integers(-1000, -1, size=(5, n1 + 1), dtype=np.int64)
+    full = CudaTensor.ofNumpy(arr.copy())
+    full.Backend.MaskedSet(full, [c0, c1], CudaTensor.ofNumpy(vals))
+    want = arr.copy()
+    want[np.ix_(m0, m1)] = vals[:3, :n1]
+    np.testing.assert_array_equal(full.toNumpy(), want)
+
+
 def test_compaction_with_32768_position_tiles(cuda_dev):
     """Inputs of >= ~58 M positions use 32768 positions per CTA (4 staging rounds). DN_COMPACT_ROUNDS=4 forces that
     configuration so the compaction tests above also cover it at sizes the oracle finishes in seconds."""
