@@ -372,7 +372,7 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
     using State = typename Op::State;
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int ROUND = 32 * VEC;
-    constexpr int UNR = 4;
+    constexpr int UNR = sizeof(T) >= 4 ? 4 : (sizeof(T) == 2 ? 2 : 1);
     constexpr bool kVecArg = sizeof(T) >= 4;  // arg folds per vector (below)
     State st = Op::identity();
     int64_t last_nan = -1;  // ordered ops only: index of the last NaN seen by the WARP (uniform)
@@ -572,7 +572,7 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
 // for a fifth CTA and serialises the loads — measured 5-7 % slower on C3). Sub-word types need more and get no
 // hint; the fused value+index fold fits with 12 bytes of spill and is 24 % faster for it (C3 Max+ArgMax in one pass:
 // 4.56 -> 5.67 TB/s, same box, `profiles/r02w_ab_reduce.txt`).
-template <class Op> struct RowsMinBlocks { static constexpr int value = sizeof(typename Op::In) >= 4 ? 4 : 1; };
+template <class Op> struct RowsMinBlocks { static constexpr int value = sizeof(typename Op::In) >= 4 ? 4 : 2; };
 template <class T, bool IsMax> struct RowsMinBlocks<MinMaxArgOp<T, IsMax>> { static constexpr int value = 4; };
 
 // parts == 1: warp per row.  parts == 8*S: one CTA per (row, s); its 8 warps take consecutive parts.

@@ -49,6 +49,24 @@ out["f64 131072x1000 argmax"] = 131072 * 8000 / timed(lambda: oid._fill_axis("Ar
 ti8 = torch.randint(-100, 100, (262144, 1000), device="cuda", dtype=torch.int8)
 l8 = w(ti8, dtypes.DN_I8)
 out["i8 262144x1000 argmax"] = 262144 * 1000 / timed(lambda: oi._fill_axis("ArgMaxLastAxis", 1, l8, True)) / 1e6
+o8 = Tensor.empty((262144,), dtypes.DN_I8, dev)
+out["i8 262144x1000 sum"] = 262144 * 1000 / timed(lambda: o8.FillSumAxis(1, l8)) / 1e6
+out["i8 262144x1000 max"] = 262144 * 1000 / timed(lambda: o8.FillMaxAxis(1, l8)) / 1e6
+ti16 = torch.randint(-1000, 1000, (262144, 1000), device="cuda", dtype=torch.int16)
+l16 = w(ti16, dtypes.DN_I16); o16 = Tensor.empty((262144,), dtypes.DN_I16, dev)
+out["i16 262144x1000 max"] = 262144 * 2000 / timed(lambda: o16.FillMaxAxis(1, l16)) / 1e6
+out["i16 262144x1000 argmax"] = 262144 * 2000 / timed(lambda: oi._fill_axis("ArgMaxLastAxis", 1, l16, True)) / 1e6
+tb = torch.rand(262144, 1000, device="cuda") < 0.5
+lb = w(tb, dtypes.DN_BOOL); ob = Tensor.empty((262144,), dtypes.DN_BOOL, dev)
+out["bool 262144x1000 countTrue"] = 262144 * 1000 / timed(lambda: oi._fill_axis("CountTrueLastAxis", 1, lb, True)) / 1e6
+out["bool 262144x1000 all"] = 262144 * 1000 / timed(lambda: ob.FillAllAxis(1, lb)) / 1e6
+tb2 = torch.rand(16384, 16384, device="cuda") < 0.5
+lb2 = w(tb2, dtypes.DN_BOOL); oi2 = Tensor.empty((16384,), dtypes.DN_I64, dev)
+out["bool 16384^2 countTrue1"] = 16384 * 16384 / timed(lambda: oi2._fill_axis("CountTrueLastAxis", 1, lb2, True)) / 1e6
+ti82 = torch.randint(-100, 100, (16384, 16384), device="cuda", dtype=torch.int8)
+l82 = w(ti82, dtypes.DN_I8); o82 = Tensor.empty((16384,), dtypes.DN_I8, dev)
+out["i8 16384^2 sum1"] = 16384 * 16384 / timed(lambda: o82.FillSumAxis(1, l82)) / 1e6
+del tb, tb2, ti16, ti8, ti82
 t2 = torch.rand(16384, 16384, device="cuda") * 100 - 50
 a2 = w(t2, dtypes.DN_F32); o2 = Tensor.empty((16384,), dtypes.DN_F32, dev); o2i = Tensor.empty((16384,), dtypes.DN_I64, dev)
 nb2 = 16384 * 16384 * 4
