@@ -134,6 +134,17 @@ struct SumOp {
         else return a + b;
     }
     __device__ static Out finalize(State s) { return s; }
+    // 8- and 16-bit integers: the sixteen bytes of one 128-bit load through the dot-product unit (4 x IDP.4A /
+    // IDP.2A with a vector of ones); the sum wraps in the element type, so any wider accumulator gives the same bits
+    __device__ static void packed16(State &s, const uint32_t *w) {
+        uint32_t acc = (uint32_t)(UnsignedT<T>)s;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (sizeof(T) == 1) acc = __dp4a(w[i], 0x01010101u, acc);
+            else acc = __dp2a_lo(w[i], 0x00000101u, acc);
+        }
+        s = (T)(UnsignedT<T>)acc;
+    }
 };
 
 template <class T>
@@ -228,6 +239,10 @@ struct CountTrueOp {
 template <class Op> struct HasPacked16 : std::false_type {};
 template <bool IsAll> struct HasPacked16<AllAnyOp<IsAll>> : std::true_type {};
 template <> struct HasPacked16<CountTrueOp> : std::true_type {};
+template <> struct HasPacked16<SumOp<int8_t>> : std::true_type {};
+template <> struct HasPacked16<SumOp<uint8_t>> : std::true_type {};
+template <> struct HasPacked16<SumOp<int16_t>> : std::true_type {};
+template <> struct HasPacked16<SumOp<uint16_t>> : std::true_type {};
 
 template <class T, bool IsMax>
 struct ArgOp {
@@ -361,6 +376,118 @@ template <class T, bool IsMax> struct ArgPick<MinMaxArgOp<T, IsMax>> {
 // ---------------------------------------------------------------------------------------------------------------
 // rows family
 // ---------------------------------------------------------------------------------------------------------------
+// Min / Max of 1- and 2-byte integers on two 16-bit SIMD lanes (VIMNMX.S16x2 / .U16x2 are native; the 8-bit x4 forms
+// are emulated): a lane keeps a packed 2 x 16-bit accumulator for the whole part; bytes are widened on the way in
+// (one PRMT with sign replication / a zero byte per pair) — 1 instruction per byte, 0.5 per 16-bit element.
+template <class Op> struct PackedMinMax { static constexpr bool value = false; };
+template <class T, bool IsMax> struct PackedMinMax<MinMaxIntOp<T, IsMax>> {
+    static constexpr bool value = sizeof(T) < 4;
+    static constexpr bool kSigned = std::is_signed<T>::value;
+    __device__ static uint32_t mnmx(uint32_t a, uint32_t b) {
+        if constexpr (kSigned) return IsMax ? __vmaxs2(a, b) : __vmins2(a, b);
+        else return IsMax ? __vmaxu2(a, b) : __vminu2(a, b);
+    }
+    __device__ static uint32_t identity() {  // the fold's start value in both 16-bit lanes
+        const uint32_t v = (uint32_t)(uint16_t)(int16_t)MinMaxIntOp<T, IsMax>::identity();
+        return v | (v << 16);
+    }
+    __device__ static uint32_t prmt(uint32_t a, uint32_t sel) {
+        uint32_t d;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+        return d;
+    }
+    __device__ static void fold16(uint32_t &acc, const uint32_t *w) {  // the 16 bytes of one vector
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (sizeof(T) == 2) {
+                acc = mnmx(acc, w[i]);
+            } else {  // bytes 0,2 and bytes 1,3 as 16-bit lanes (selector msb: replicate the byte's sign; 4: zero)
+                acc = mnmx(acc, prmt(w[i], kSigned ? 0xA280u : 0x4240u));
+                acc = mnmx(acc, prmt(w[i], kSigned ? 0xB391u : 0x4341u));
+            }
+        }
+    }
+    __device__ static T finish(uint32_t acc) {
+        acc = mnmx(acc, acc >> 16);
+        return (T)(uint16_t)(acc & 0xFFFFu);
+    }
+};
+
+// The same for 1- and 2-byte elements (integers and bools; never ordered). A vector holds 8 or 16 elements, so the
+// general structure below — per-element predicates in every ragged round, scalar loads assembled into vectors — costs
+// ~200 registers (one per element in flight) and one CTA per SM. Here a lane only ever folds ONE element (head up to
+// 16-byte alignment and the < VEC elements after the last whole vector, one per lane) or a WHOLE vector that stays
+// packed in four registers: ops with a packed form (Sum through the dot-product unit, All / Any / CountTrue through
+// byte-wise SIMD, Min / Max on 16-bit SIMD lanes) never unpack it. 262144 int8 rows of 1000: Sum 0.47 -> 3.35 TB/s,
+// int16 Max 0.91 -> 6.56 (profiles/r02za_ab_reduce.txt).
+template <class Op>
+__device__ __forceinline__ typename Op::State warp_fold_part_subword(const Op &op, const char *row, int64_t begin,
+                                                                    int64_t end, int lane) {
+    using T = typename Op::In;
+    using State = typename Op::State;
+    static_assert(sizeof(T) < 4 && !Op::ordered, "sub-word integer / bool folds only");
+    constexpr int VEC = 16 / (int)sizeof(T);
+    // vectors in flight per lane: bytes that are folded one by one get unpacked into a register each
+    constexpr int UNR = (HasPacked16<Op>::value || PackedMinMax<Op>::value || sizeof(T) == 2) ? 4 : 2;
+    State st = Op::identity();
+    int ridx = -1;  // arg ops: lane-local best index relative to `begin`
+    uint32_t pacc = 0;  // Min / Max: packed 2 x 16-bit accumulator
+    if constexpr (PackedMinMax<Op>::value) pacc = PackedMinMax<Op>::identity();
+    const T *p = reinterpret_cast<const T *>(row);
+    auto fold1 = [&](T v, int64_t i) {
+        if constexpr (IsArgOp<Op>::value) {
+            if (Op::better(v, st.val)) {
+                st.val = v;
+                ridx = (int)(i - begin);
+            }
+        } else {
+            op_step(op, st, v, i);
+        }
+    };
+    int64_t i = begin;
+    if (i < end) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(p + i);
+        int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
+        if (head > end - i) head = (int)(end - i);
+        if (lane < head) fold1(p[i + lane], i + lane);
+        i += head;
+        const int64_t nvec = (end - i) / VEC;  // whole vectors; vector k belongs to lane k % 32
+        const T *g = p + i;
+        for (int64_t base = 0; base < nvec; base += 32 * UNR) {
+            Pack<T, VEC> buf[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int64_t k = base + u * 32 + lane;
+                if (k < nvec) buf[u] = load_pack<Pack<T, VEC>>(reinterpret_cast<const char *>(g + k * VEC));
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int64_t k = base + u * 32 + lane;
+                if (k < nvec) {
+                    if constexpr (HasPacked16<Op>::value) {
+                        Op::packed16(st, reinterpret_cast<const uint32_t *>(buf[u].v));
+                    } else if constexpr (PackedMinMax<Op>::value) {
+                        PackedMinMax<Op>::fold16(pacc, reinterpret_cast<const uint32_t *>(buf[u].v));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) fold1(buf[u].v[j], i + k * VEC + j);
+                    }
+                }
+            }
+        }
+        const int64_t ts = i + nvec * VEC;
+        if (lane < (int)(end - ts)) fold1(p[ts + lane], ts + lane);
+    }
+    if constexpr (PackedMinMax<Op>::value) st = Op::combine(st, PackedMinMax<Op>::finish(pacc));
+    if constexpr (IsArgOp<Op>::value) {
+        warp_arg_combine32<T, IsMaxOp<Op>::value>(st.val, ridx);
+        st.idx = ridx >= 0 ? begin + ridx : (int64_t)DN_NOT_FOUND;
+        return st;
+    } else {
+        return warp_combine_unordered<Op>(st);
+    }
+}
+
 // One warp folds elements [begin, end) of a contiguous row. All lanes return the same state.
 // Structure: scalar head up to 16-byte alignment, then rounds of 32*VEC consecutive elements (lane l owns VEC
 // consecutive elements of a round), UNR rounds loaded before any is folded; the last group is the same code with
@@ -370,9 +497,10 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
                                                             int64_t end, int lane) {
     using T = typename Op::In;
     using State = typename Op::State;
+    if constexpr (sizeof(T) < 4) return warp_fold_part_subword<Op>(op, row, begin, end, lane);
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int ROUND = 32 * VEC;
-    constexpr int UNR = sizeof(T) >= 4 ? 4 : (sizeof(T) == 2 ? 2 : 1);
+    constexpr int UNR = 4;
     constexpr bool kVecArg = sizeof(T) >= 4;  // arg folds per vector (below)
     State st = Op::identity();
     int64_t last_nan = -1;  // ordered ops only: index of the last NaN seen by the WARP (uniform)
@@ -569,10 +697,12 @@ __device__ __forceinline__ typename Op::State warp_fold_part(const Op &op, const
 
 // Register target of the rows kernel: the folds over 4- and 8-byte elements need <= 64 registers and run best at
 // exactly that (4 CTAs per SM: the loads of a group stay in flight; left alone ptxas squeezes them to 48 registers
-// for a fifth CTA and serialises the loads — measured 5-7 % slower on C3). Sub-word types need more and get no
-// hint; the fused value+index fold fits with 12 bytes of spill and is 24 % faster for it (C3 Max+ArgMax in one pass:
+// for a fifth CTA and serialises the loads — measured 5-7 % slower on C3). Byte-wise folds that unpack their
+// vectors (ArgMin/ArgMax, Find, Product of 1-byte elements) get 85; the fused value+index fold fits with 12 bytes of spill and is 24 % faster for it (C3 Max+ArgMax in one pass:
 // 4.56 -> 5.67 TB/s, same box, `profiles/r02w_ab_reduce.txt`).
-template <class Op> struct RowsMinBlocks { static constexpr int value = sizeof(typename Op::In) >= 4 ? 4 : 2; };
+template <class Op> struct RowsMinBlocks {
+    static constexpr int value = (sizeof(typename Op::In) == 1 && !HasPacked16<Op>::value && !PackedMinMax<Op>::value) ? 3 : 4;
+};
 template <class T, bool IsMax> struct RowsMinBlocks<MinMaxArgOp<T, IsMax>> { static constexpr int value = 4; };
 
 // parts == 1: warp per row.  parts == 8*S: one CTA per (row, s); its 8 warps take consecutive parts.

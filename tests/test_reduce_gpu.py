@@ -63,6 +63,45 @@ def test_all_numeric_dtypes(cuda_dev, dtype):
         assert_same(h.productAxis(1), c.productAxis(1), dtype, what="productAxis int")
 
 
+SUBWORD = [dtypes.DN_I8, dtypes.DN_U8, dtypes.DN_I16, dtypes.DN_U16]
+
+
+@pytest.mark.parametrize("dtype", SUBWORD)
+def test_subword_rows_full_range(cuda_dev, dtype):
+    """1- and 2-byte integers take their own row fold (whole 16-byte vectors kept packed — Sum through the
+    dot-product unit — plus one element per lane for the misaligned head and the ragged tail): full-range values so
+    that the wrapping sums matter, row lengths around every vector / warp-round boundary, rows that start at every
+    byte alignment (odd row length and a sliced first column), and a long single row (several parts per row)."""
+    info = np.iinfo(dtypes.to_numpy(dtype))
+    rng = np.random.default_rng(29)
+    for rows, L in [(37, 1), (37, 15), (37, 16), (37, 17), (37, 31), (64, 511), (64, 512), (64, 513), (29, 1000),
+                    (11, 2047), (11, 2049), (5, 4099), (3, 70001), (1, 300007)]:
+        arr = rng.integers(info.min, int(info.max) + 1, size=(rows, L + 3), dtype=np.int64).astype(info.dtype)
+        h0, c0 = pair(arr)
+        for h, c, tag in [(h0, c0, "whole rows"), (h0[:, 3:], c0[:, 3:], "first column 3"), (h0[:, 1:L], c0[:, 1:L], "inner slice")]:
+            if h.Shape[1] == 0:
+                continue
+            what = f"{tag} {rows}x{L}"
+            assert_same(h.sumAxis(1), c.sumAxis(1), dtype, what="sumAxis " + what)
+            assert_same(h.productAxis(1), c.productAxis(1), dtype, what="productAxis " + what)
+            assert_same(h.maxAxis(1), c.maxAxis(1), dtype, what="maxAxis " + what)
+            assert_same(h.minAxis(1), c.minAxis(1), dtype, what="minAxis " + what)
+            assert_same(h.argMaxAxis(1), c.argMaxAxis(1), dtypes.DN_I64, what="argMaxAxis " + what)
+            assert_same(h.argMinAxis(1), c.argMinAxis(1), dtypes.DN_I64, what="argMinAxis " + what)
+            v = arr[0, L // 2].item()
+            assert_same(h.findAxis(v, 1), c.findAxis(v, 1), dtypes.DN_I64, what="findAxis " + what)
+    # extremes: rows of the initial value (ArgMax of all-lowest is NotFound), ties (first occurrence)
+    arr = np.full((4, 1000), info.min, dtype=info.dtype)
+    arr[1, 700] = arr[1, 900] = info.max
+    arr[2, :] = info.max
+    arr[3, 999] = info.min + 1
+    h, c = pair(arr)
+    assert_same(h.argMaxAxis(1), c.argMaxAxis(1), dtypes.DN_I64, what="argMax extremes")
+    assert_same(h.argMinAxis(1), c.argMinAxis(1), dtypes.DN_I64, what="argMin extremes")
+    assert_same(h.maxAxis(1), c.maxAxis(1), dtype, what="max extremes")
+    assert_same(h.sumAxis(1), c.sumAxis(1), dtype, what="sum extremes")
+
+
 @pytest.mark.parametrize("dtype", FLOATS)
 def test_product_float(cuda_dev, dtype):
     rng = np.random.default_rng(23)
