@@ -303,6 +303,29 @@ def measure_other_configs(dev, torch, peak):
         o1.FillSumAxis(1, c)
     hbm("C1 FUSED a*b+sin(a) (1 call, dn_fused_elemwise) + SumLastAxis 4096x4096 [bytes of the fused form]",
         4 * n1 + 4096 * 4, c1_fused, 8)
+    # the same calls captured once into a CUDA graph and replayed: the library's entry points only enqueue work on the
+    # caller's stream (no synchronisation, no host allocation), so a host that replays a fixed sequence pays one graph
+    # launch instead of one ctypes / P-Invoke call + kernel launch per operator
+    try:
+        side = torch.cuda.Stream()
+        graphs = []
+        for fn in (c1, c1_fused):
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                dev.SetStream(side.cuda_stream)
+                fn()
+            dev.SetStream(stream.cuda_stream)
+            graphs.append(g)
+        dev.api.call("release_stream", side.cuda_stream)
+        hbm("C1 a*b+sin(a) (3 calls) + SumLastAxis 4096x4096, the 4 launches replayed from a CUDA graph", 9 * n1 + 4096 * 4,
+            graphs[0].replay, 8)
+        hbm("C1 FUSED a*b+sin(a) + SumLastAxis 4096x4096, the 2 launches replayed from a CUDA graph", 4 * n1 + 4096 * 4,
+            graphs[1].replay, 8)
+        del graphs
+    except Exception as exc:  # reported, never fatal for the bench line
+        dev.SetStream(stream.cuda_stream)
+        out["C1 replayed from a CUDA graph"] = {"error": str(exc)[:200]}
     td = torch.rand(8192, 8192, device="cuda", dtype=torch.float64) * 100 - 50
     dd, dc = w(td, dtypes.DN_F64), Tensor.empty((8192, 8192), dtypes.DN_F64, dev)
     hbm("float64 sin 8192x8192 (FP64-compute-bound on B200, not an HBM kernel)", 2 * 8 * 8192 * 8192, lambda: dc.FillSin(dd))

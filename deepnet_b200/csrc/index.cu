@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(kIdxThreads) scatter_kernel(const __grid_const
 constexpr int kBinThreads = 512;
 constexpr int kBinSmemBytes = 64 * 1024;
 constexpr int kMaxBins = 8192;
+constexpr uint32_t kSpreadBins = 64;  // histogram passes with at most this many bins keep one counter column per lane
 
 struct BinParams {
     GSParams gs;
@@ -253,7 +254,13 @@ __device__ __forceinline__ bool bin_target(const BinParams &p, uint32_t f, int64
 template <bool PAIRS, int NDI, int NDO>
 __global__ void __launch_bounds__(kBinThreads) scatter_hist_kernel(const __grid_constant__ BinParams p) {
     extern __shared__ uint32_t sh_hist[];
-    for (uint32_t b = threadIdx.x; b < p.nbins; b += kBinThreads) sh_hist[b] = 0;
+    // Few bins (level 1: <= 64 coarse bins): 512 threads adding into a handful of counters collide on the same address
+    // all the time, and shared-memory atomics serialise those. Every lane gets its own column of counters instead
+    // (counter = bin * 32 + lane: distinct addresses AND distinct banks inside a warp), summed at the end.
+    const bool spread = p.nbins <= kSpreadBins;
+    const uint32_t ncounters = spread ? p.nbins * 32 : p.nbins;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t b = threadIdx.x; b < ncounters; b += kBinThreads) sh_hist[b] = 0;
     __syncthreads();
     const uint64_t begin = (uint64_t)blockIdx.x * p.chunk;
     uint64_t end = begin + p.chunk;
@@ -281,12 +288,24 @@ __global__ void __launch_bounds__(kBinThreads) scatter_hist_kernel(const __grid_
             // an element with an out-of-range index raises the error flag and travels on as "add 0 to element 0",
             // so that both levels see the same number of elements
             if (state[j] == 2) { atomicExch(p.gs.err, 1); lin[j] = 0; }
-            if (state[j] != 0) atomicAdd(&sh_hist[lin[j] >> p.bin_log], 1u);
+            if (state[j] != 0) {
+                const uint32_t bin = lin[j] >> p.bin_log;
+                atomicAdd(&sh_hist[spread ? bin * 32 + lane : bin], 1u);
+            }
         }
     }
     __syncthreads();
     uint32_t *out = p.cta_hist + (uint64_t)blockIdx.x * p.nbins;
-    for (uint32_t b = threadIdx.x; b < p.nbins; b += kBinThreads) out[b] = sh_hist[b];
+    if (spread) {
+        for (uint32_t b = threadIdx.x; b < p.nbins; b += kBinThreads) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (uint32_t l = 0; l < 32; ++l) sum += sh_hist[b * 32 + ((l + b) & 31)];
+            out[b] = sum;
+        }
+    } else {
+        for (uint32_t b = threadIdx.x; b < p.nbins; b += kBinThreads) out[b] = sh_hist[b];
+    }
 }
 
 // bin_count[b] = sum over the CTAs' histograms (one thread per bin, four independent loads in flight).
@@ -526,22 +545,14 @@ bool dense_row_major(const dn_tensor *t) {
 // hist -> offsets -> scan -> (cursors = bin starts) -> staged partition for one level.
 template <bool PAIRS, bool FINAL, class TS, class TA>
 dn_status scatter_partition_level(BinParams &p, int grid) {
-    const size_t hist_smem = (size_t)p.nbins * 4;
+    const size_t hist_smem = (size_t)(p.nbins <= kSpreadBins ? p.nbins * 32 : p.nbins) * 4;
     DN_GS_RANK_DISPATCH(p.gs.nd_it, p.gs.nd_other,
                         DN_LAUNCH((scatter_hist_kernel<PAIRS, NDI, NDO>), grid, kBinThreads, hist_smem, p));
     DN_LAUNCH(scatter_offsets_kernel, (unsigned)((p.nbins + 255) / 256), 256, 0, p.cta_hist, p.bin_start, p.nbins, (uint32_t)grid);
     DN_LAUNCH(scatter_scan_kernel, 1, 1024, 0, p.bin_start, p.nbins);
     DN_CUDA_TRY(cudaMemcpyAsync(p.cursor, p.bin_start, (size_t)p.nbins * 4, cudaMemcpyDeviceToDevice, current_stream()));
     const int part_smem = (int)sizeof(PartitionSmem<TA>);
-    static std::atomic<bool> configured[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        DN_GS_RANK_DISPATCH(p.gs.nd_it, p.gs.nd_other,
-                            cudaFuncSetAttribute(scatter_partition_kernel<PAIRS, FINAL, TS, TA, NDI, NDO>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, part_smem));
-        // (the attribute is per kernel instantiation and device; a different rank pair sets it again below)
-    }
+    // (the attribute is per kernel instantiation and device: set before every launch, it is a host-side table write)
     DN_GS_RANK_DISPATCH(p.gs.nd_it, p.gs.nd_other,
                         cudaFuncSetAttribute(scatter_partition_kernel<PAIRS, FINAL, TS, TA, NDI, NDO>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, part_smem));
