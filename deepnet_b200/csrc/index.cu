@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kBinThreads) scatter_hist_kernel(const __grid_
     const uint64_t begin = (uint64_t)blockIdx.x * p.chunk;
     uint64_t end = begin + p.chunk;
     if (end > p.n) end = p.n;
-    constexpr int U = 4;  // loads of four positions in flight per thread
+    constexpr int U = 8;  // loads of eight positions in flight per thread (four: 2.1 TB/s over the index tensor)
     for (uint64_t base = begin; base < end; base += (uint64_t)kBinThreads * U) {
         uint32_t lin[U];
         int state[U];
@@ -587,7 +587,7 @@ dn_status scatter_binned(const GSParams &gs, const dn_tensor *acc, int64_t nt, b
     p.nt = (uint64_t)nt;
     const int nctas = sm_count() * 2;
     uint32_t chunk = (uint32_t)(((uint64_t)gs.n + nctas - 1) / nctas);
-    chunk = (chunk + kBinThreads * 4 - 1) / (kBinThreads * 4) * (kBinThreads * 4);
+    chunk = (chunk + kBinThreads * 8 - 1) / (kBinThreads * 8) * (kBinThreads * 8);
     p.chunk = chunk;
     const int grid = (int)(((uint64_t)gs.n + chunk - 1) / chunk);
     void *s_hist = nullptr, *s_start = nullptr, *s_start1 = nullptr, *s_cursor = nullptr, *s_lin = nullptr, *s_vals1 = nullptr,

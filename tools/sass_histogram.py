@@ -13,11 +13,14 @@ TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 TARGETS = [
     ("gemm.o", r"gemm_tf32_kernelILi256ELb0ELb0ELb0", "gemm_tf32_bn256"),
     ("gemm.o", r"gemm_tf32_kernelILi128ELb0ELb0ELb1", "gemm_3xtf32_bn128"),
-    ("gemm.o", r"gemm_tf32_2cta_kernelILb0ELb0", "gemm_2cta"),
+    ("gemm.o", r"gemm_tf32_2cta_kernelILb0ELb0ELb0", "gemm_2cta"),
     ("ew_binary.o", r"ew_kernelINS_7BinaryFIfLi0EEELi8", "ew_add_f32_vec8"),
     ("ew_binary.o", r"ew_xpose_kernelINS_7BinaryFIfLi0", "ew_xpose_add_f32"),
     ("reduce_arg.o", r"reduce_rows_kernelINS_5ArgOpIfLb1", "reduce_rows_argmax_f32"),
     ("shard.o", r"reduce_rows_kernelINS_11MinMaxArgOpIfLb1", "reduce_rows_max_argmax_f32"),
+    ("reduce.o", r"reduce_rows_kernelINS_5SumOpIaE", "reduce_rows_sum_i8"),
+    ("reduce.o", r"reduce_rows_kernelINS_11MinMaxIntOpIaLb1", "reduce_rows_max_i8"),
+    ("gemm.o", r"gemm_tf32_2cta_kernelILb0ELb0ELb1", "gemm_3xtf32_2cta"),
     ("shard.o", r"peer_push_kernel|peer_barrier_kernel", "shard_push_barrier"),
     ("index.o", r"compact_kernelINS_11CoordSink2DELb1ELi4", "compact_trueidx2d"),
     ("index.o", r"scatter_(hist|partition|accumulate)_kernel", "scatter_binned"),
