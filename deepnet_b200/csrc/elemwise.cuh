@@ -689,7 +689,10 @@ dn_status ew_launch_xpose(const EwPlan &plan, const F &f, int dS) {
     constexpr int NOPS = F::NSRC + 1;
     // micro-tile: 4x4 elements, 2x2 when an 8-byte type is involved (vectors stay <= 16 bytes)
     constexpr int M = F::MaxSize >= 8 ? 2 : 4;
-    constexpr int K = F::MaxSize >= 8 ? 4 : 1;
+    // micro-tiles per thread: 8-byte types 4 (128 bytes per operand in flight); 4-byte types 2 for one-source
+    // operators (copy a.T / abs(a.T): +3-4 %), 1 for two sources (2 costs a.T + b 2 %, a < b.T 3 %:
+    // profiles/r02zg_ab_xpose.txt)
+    constexpr int K = F::MaxSize >= 8 ? 4 : (F::NSRC == 1 ? 2 : 1);
     EwXposeParams<NOPS> p;
     const int nd = plan.ndims;
     p.sizeT = (uint32_t)plan.shape[0];
