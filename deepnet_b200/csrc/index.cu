@@ -1042,6 +1042,7 @@ __global__ void __launch_bounds__(kCompactThreads, ROUNDS == 1 ? 6 : 4) compact_
         return (int64_t)s_base;
     };
 
+    const uint32_t staged_base = (uint32_t)__cvta_generic_to_shared(staged);
     int64_t base = 0;
     bool have_base = false;
     if constexpr (Sink::kLoadNeedsRank) {
@@ -1055,11 +1056,18 @@ __global__ void __launch_bounds__(kCompactThreads, ROUNDS == 1 ? 6 : 4) compact_
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const uint32_t b = bits[2 * r + h];
-            uint32_t at = local[2 * r + h];
             const uint32_t off0 = h * kChunkElems + threadIdx.x * kItems;
+            // predicated, no divergent loop; the slot is a 32-bit shared-window address that is bumped by two — three
+            // instructions per position (test, store, add). Indexing `staged[at++]` made the compiler rebuild the
+            // generic address for every store (S2R + MOV + LEA): ~8 instructions per position, 55 % of all the
+            // kernel issued on a sparse mask (profiles/r02c_compact_trueidx_sparse: 15 instructions per position).
+            uint32_t slot = staged_base + local[2 * r + h] * 2;
 #pragma unroll
-            for (int j = 0; j < kItems; ++j)  // predicated, no divergent loop
-                if ((b >> j) & 1u) staged[at++] = (uint16_t)(off0 + j);
+            for (int j = 0; j < kItems; ++j)
+                if ((b >> j) & 1u) {
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(slot), "h"((uint16_t)(off0 + j)) : "memory");
+                    slot += 2;
+                }
         }
         __syncthreads();
         // Consecutive threads own consecutive ranks: dense-side accesses are fully coalesced; U loads in flight.
