@@ -1,7 +1,10 @@
 """A/B timing of the C3 reductions with two builds of the library on the SAME box (clocks and power caps differ from
 box to box by a few percent, which is the size of the effects being chased):
     python tools/ab_reduce.py build/ab/libdeepnet_b200_r01.so deepnet_b200/lib/libdeepnet_b200.so
-Each library runs in its own process, alternating, three rounds; CUDA-event timing of 20 back-to-back calls."""
+Each library runs in its own process, alternating, three rounds; CUDA-event timing of 20 back-to-back calls.
+An older build for the left column: `git archive <rev> | tar -x -C build/ab_src && make -C build/ab_src -j &&
+cp build/ab_src/deepnet_b200/lib/libdeepnet_b200.so build/ab/libdeepnet_b200_<rev>.so` (build/ is git-ignored but travels
+to the GPU box). tools/ab_xpose.py is the same harness for the transposed-view element-wise kernels."""
 import json
 import os
 import subprocess
